@@ -1,0 +1,421 @@
+// tcgen05 / TMA GEMM family (see gemm_tc.h).  One CTA computes a 128 x BN output tile:
+//   warp 0 : TMA producer (one elected lane) - fills a ring of {A 128x64, W BNx64} stages
+//   warp 1 : TMEM allocator + tcgen05.mma issuer (one elected lane), accumulator in TMEM
+//   warps 2-5 : epilogue, one TMEM lane quarter each: tcgen05.ld -> bias/act/layer-scale/residual ->
+//               16-bit (or fp32) rows to global, with optional row re-ordering / pixel shuffle.
+// Replaces, on the LW-DETR path, every F.linear / nn.Conv2d / nn.ConvTranspose2d call listed in
+// SURVEY.md appendix B (reference: models/backbone/vit.py:120-140,206-220, projector.py:85-132,
+// transformer.py:27-39,466-517, ops/modules/ms_deform_attn.py:112-143, lwdetr.py:149-159).
+#include "gemm_tc.h"
+#include "ptx.cuh"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+
+namespace lwb {
+
+static constexpr int BM = 128;
+static constexpr int BK = 64;
+static constexpr int A_STAGE_BYTES = BM * BK * 2;
+static constexpr int GEMM_THREADS = 192;
+
+__device__ __forceinline__ float apply_act(float v, int act) {
+  if (act == ACT_RELU) return fmaxf(v, 0.f);
+  if (act == ACT_GELU) return 0.5f * v * (1.f + erff(v * 0.70710678118654752f));
+  if (act == ACT_SILU) return v / (1.f + __expf(-v));
+  return v;
+}
+
+template <typename T, int BN>
+__global__ void __launch_bounds__(GEMM_THREADS)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmArgs p) {
+  constexpr int B_STAGE_BYTES = BN * BK * 2;
+  constexpr uint32_t TMEM_COLS = BN <= 64 ? 64 : (BN <= 128 ? 128 : 256);
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int stages = p.stages;
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + stages * A_STAGE_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sB + stages * B_STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + stages;
+  uint64_t* acc_bar = empty_bar + stages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_bar + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int n_tile = blockIdx.x % p.n_tiles;
+  const int m_tile = blockIdx.x / p.n_tiles;
+  const int n0 = n_tile * BN;
+
+  // conv tile decode (also used by the epilogue)
+  int cb = 0, cy0 = 0, cx0 = 0;
+  if (p.a_mode != AMODE_PLAIN) {
+    const int per_img = p.tiles_x * p.tiles_y;
+    cb = m_tile / per_img;
+    const int t = m_tile % per_img;
+    cy0 = (t / p.tiles_x) * p.TH;
+    cx0 = (t % p.tiles_x) * p.TW;
+  }
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < stages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(acc_bar, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ------------------------------------------------------------------ TMA producer
+      for (int kb = 0; kb < p.kblocks; ++kb) {
+        const int s = kb % stages;
+        const uint32_t ph = (kb / stages) & 1;
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        mbar_arrive_expect_tx(&full_bar[s], p.a_stage_tx + B_STAGE_BYTES);
+        uint8_t* a_dst = sA + s * A_STAGE_BYTES;
+        if (p.a_mode == AMODE_PLAIN) {
+          tma_load_2d(a_dst, &tmA, &full_bar[s], kb * BK, m_tile * BM);
+        } else {
+          const int tap = kb / p.cin_blocks;
+          const int c0 = (kb % p.cin_blocks) * BK;
+          const int dy = tap / 3, dx = tap % 3;
+          if (p.a_mode == AMODE_CONV3_S1) {
+            tma_load_4d(a_dst, &tmA, &full_bar[s], c0, cx0 + dx - 1, cy0 + dy - 1, cb);
+          } else {
+            // input row iy = 2*oy + dy - 1 = 2*(oy + yoff) + py ; same for columns
+            const int py = (dy == 1) ? 0 : 1, yoff = (dy == 0) ? -1 : 0;
+            const int px = (dx == 1) ? 0 : 1, xoff = (dx == 0) ? -1 : 0;
+            tma_load_5d(a_dst, &tmA, &full_bar[s], px * p.lda + c0, cx0 + xoff, py, cy0 + yoff, cb);
+          }
+        }
+        tma_load_2d(sB + s * B_STAGE_BYTES, &tmB, &full_bar[s], kb * BK, n0);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ------------------------------------------------------------------ MMA issuer
+      constexpr uint32_t idesc = umma_idesc_f16(Cvt<T>::is_bf16, BM, BN);
+      for (int kb = 0; kb < p.kblocks; ++kb) {
+        const int s = kb % stages;
+        const uint32_t ph = (kb / stages) & 1;
+        mbar_wait(&full_bar[s], ph);
+        tc_fence_after();
+        const uint64_t adesc = umma_desc_k128(smem_u32(sA + s * A_STAGE_BYTES));
+        const uint64_t bdesc = umma_desc_k128(smem_u32(sB + s * B_STAGE_BYTES));
+#pragma unroll
+        for (int k = 0; k < BK / 16; ++k) {
+          // advance 16 elements (32 B) along K inside the 128 B swizzle row: +2 in 16-byte units
+          umma_f16_ss(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+        }
+        umma_commit(&empty_bar[s]);
+      }
+      umma_commit(acc_bar);
+    }
+  } else {
+    // -------------------------------------------------------------------- epilogue
+    const int quarter = warp & 3;               // TMEM lanes [32*quarter, 32*quarter+32)
+    const int r = quarter * 32 + lane;          // row inside the tile
+    int m, b = 0, y = 0, x = 0;
+    bool valid;
+    if (p.a_mode == AMODE_PLAIN) {
+      m = m_tile * BM + r;
+      valid = m < p.M;
+      if (p.remap_rows || p.shuffle_cout) {
+        const int per = p.IH * p.IW;
+        b = m / per;
+        const int rem = m - b * per;
+        if (p.rows_in == ROWS_WINDOW_MAJOR) {
+          const int wh = p.IH >> 2, ww = p.IW >> 2, wsz = wh * ww;
+          const int win = rem / wsz, t = rem - win * wsz;
+          y = (win >> 2) * wh + t / ww;
+          x = (win & 3) * ww + t % ww;
+        } else {
+          y = rem / p.IW;
+          x = rem - y * p.IW;
+        }
+      }
+    } else {
+      const int ry = r / p.TW;
+      y = cy0 + ry;
+      x = cx0 + (r - ry * p.TW);
+      b = cb;
+      valid = (r < p.TW * p.TH) && (y < p.OH) && (x < p.OW);
+      m = (b * p.OH + y) * p.OW + x;
+    }
+    long long out_row = m;
+    if (p.remap_rows) out_row = (static_cast<long long>(b) * p.IH + y) * p.IW + x;
+    const long long res_row = p.resid_mod > 0 ? (m % p.resid_mod) : m;
+
+    mbar_wait(acc_bar, 0);
+    tc_fence_after();
+    const uint32_t taddr_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
+
+#pragma unroll 1
+    for (int c = 0; c < BN / 16; ++c) {
+      float v[16];
+      __syncwarp();                               // tcgen05.ld is .sync.aligned: reconverge first
+      tmem_ld_x16(taddr_row + c * 16, v);
+      tmem_ld_wait();
+      const int n = n0 + c * 16;
+      if (!valid || n >= p.N) continue;
+      const int nrem = p.N - n;   // >= 1
+      // bias, activation
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        float t = v[j];
+        if (p.bias != nullptr && j < nrem) t += __ldg(p.bias + n + j);
+        v[j] = apply_act(t, p.act);
+      }
+      if (p.gamma != nullptr) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          if (j < nrem) v[j] *= __ldg(p.gamma + n + j);
+      }
+      if (p.resid != nullptr) {
+        const T* rp = reinterpret_cast<const T*>(p.resid) + res_row * p.ld_resid + n;
+        if (nrem >= 16 && (reinterpret_cast<uintptr_t>(rp) & 31) == 0) {
+          const U8 rr = ldg256(rp);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float2 f = Cvt<T>::unpack(rr.v[j]);
+            v[2 * j] += f.x;
+            v[2 * j + 1] += f.y;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (j < nrem) v[j] += Cvt<T>::to_f(rp[j]);
+        }
+      }
+      // destination
+      long long orow = out_row;
+      int ocol = n;
+      if (p.shuffle_cout > 0) {
+        const int q = n / p.shuffle_cout;
+        ocol = n - q * p.shuffle_cout;
+        orow = (static_cast<long long>(b) * (2 * p.IH) + 2 * y + (q >> 1)) * (2 * p.IW) + 2 * x + (q & 1);
+      }
+      if (p.out_fp32) {
+        float* op = reinterpret_cast<float*>(p.out) + orow * p.ld_out + ocol;
+        if (nrem >= 16 && (reinterpret_cast<uintptr_t>(op) & 15) == 0) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            reinterpret_cast<float4*>(op)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (j < nrem) op[j] = v[j];
+        }
+      } else {
+        T* op = reinterpret_cast<T*>(p.out) + orow * p.ld_out + ocol;
+        if (nrem >= 16 && (reinterpret_cast<uintptr_t>(op) & 31) == 0) {
+          U8 o;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o.v[j] = Cvt<T>::pack(v[2 * j], v[2 * j + 1]);
+          stg256(op, o);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (j < nrem) op[j] = Cvt<T>::from_f(v[j]);
+        }
+      }
+    }
+    tc_fence_before();
+  }
+
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+// ------------------------------------------------------------------------------------------- host
+typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                        const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                        CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                        CUtensorMapFloatOOBfill);
+
+static PFN_tmapEncodeTiled encode_fn() {
+  static PFN_tmapEncodeTiled fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      p = nullptr;
+    return reinterpret_cast<PFN_tmapEncodeTiled>(p);
+  }();
+  return fn;
+}
+
+static int encode(CUtensorMap* tm, int dtype, int rank, const void* base, const cuuint64_t* dims,
+                  const cuuint64_t* strides_bytes, const cuuint32_t* box, std::string* err) {
+  PFN_tmapEncodeTiled fn = encode_fn();
+  if (!fn) {
+    *err = "cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)";
+    return -1;
+  }
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = fn(tm, dtype == DT_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16,
+                  static_cast<cuuint32_t>(rank), const_cast<void*>(base), dims, strides_bytes, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char buf[256];
+    snprintf(buf, sizeof buf, "cuTensorMapEncodeTiled failed (CUresult %d, rank %d, dim0 %llu, stride1 %llu, box0 %u)",
+             static_cast<int>(r), rank, (unsigned long long)dims[0],
+             (unsigned long long)(rank > 1 ? strides_bytes[0] : 0), box[0]);
+    *err = buf;
+    return -1;
+  }
+  return 0;
+}
+
+static int pick_bn(int N, int m_tiles) {
+  int bn;
+  if (N <= 64) bn = 64;
+  else if (N <= 128) bn = 128;
+  else {
+    const int cand[3] = {256, 192, 128};
+    int best = 256, best_waste = 1 << 30;
+    for (int c : cand) {
+      const int waste = ((N + c - 1) / c) * c - N;
+      if (waste < best_waste) { best_waste = waste; best = c; }
+    }
+    bn = best;
+  }
+  // Small problems: prefer more CTAs over wider tiles so that all 148 SMs get work.
+  auto tiles = [&](int b) { return static_cast<long long>(m_tiles) * ((N + b - 1) / b); };
+  while (bn > 64 && tiles(bn) < 148) {
+    const int nb = bn == 256 ? 128 : (bn == 192 ? 64 : 64);
+    if (((N + nb - 1) / nb) * nb - N > ((N + bn - 1) / bn) * bn - N + 32) break;
+    bn = nb;
+  }
+  return bn;
+}
+
+int gemm_build(const GemmDesc& d, GemmOp* op, std::string* err) {
+  std::memset(op, 0, sizeof(*op));
+  if (d.K % BK != 0 || d.K <= 0) { *err = "gemm: K must be a positive multiple of 64"; return -1; }
+  if (!d.out_fp32 && (d.ld_out % 8) != 0) { *err = "gemm: 16-bit ld_out must be a multiple of 8"; return -1; }
+  if ((d.lda % 8) != 0) { *err = "gemm: lda must be a multiple of 8"; return -1; }
+  GemmArgs& a = op->args;
+  a.M = d.M; a.N = d.N; a.kblocks = d.K / BK; a.a_mode = d.a_mode; a.lda = d.lda;
+  a.bias = d.bias; a.gamma = d.gamma; a.resid = d.resid; a.ld_resid = d.ld_resid; a.resid_mod = d.resid_mod;
+  a.act = d.act; a.out = d.out; a.ld_out = d.ld_out; a.out_fp32 = d.out_fp32;
+  a.rows_in = d.rows_in; a.remap_rows = d.remap_rows; a.shuffle_cout = d.shuffle_cout; a.IH = d.IH; a.IW = d.IW;
+  op->dtype = d.dtype;
+  if ((d.remap_rows || d.shuffle_cout) && (d.IH <= 0 || d.IW <= 0 || d.M % (d.IH * d.IW) != 0)) {
+    *err = "gemm: row remap needs IH/IW with M a multiple of IH*IW"; return -1;
+  }
+  if (d.rows_in == ROWS_WINDOW_MAJOR && ((d.IH % 4) || (d.IW % 4))) { *err = "gemm: window grid needs IH,IW % 4 == 0"; return -1; }
+  if (d.shuffle_cout > 0 && (d.shuffle_cout % 16 != 0 || d.N != 4 * d.shuffle_cout)) {
+    *err = "gemm: pixel-shuffle needs N == 4*cout, cout % 16 == 0"; return -1;
+  }
+
+  int m_tiles;
+  if (d.a_mode == AMODE_PLAIN) {
+    m_tiles = (d.M + BM - 1) / BM;
+    a.a_stage_tx = A_STAGE_BYTES;
+    const cuuint64_t dims[2] = {static_cast<cuuint64_t>(d.K), static_cast<cuuint64_t>(d.M)};
+    const cuuint64_t strides[1] = {static_cast<cuuint64_t>(d.lda) * 2};
+    const cuuint32_t box[2] = {BK, BM};
+    if (encode(&op->ta, d.dtype, 2, d.A, dims, strides, box, err)) return -1;
+  } else {
+    if (d.K % 9 != 0 || (d.K / 9) % BK != 0) { *err = "gemm: conv needs K = 9*Cin, Cin % 64 == 0"; return -1; }
+    if (d.M != d.B * d.OH * d.OW) { *err = "gemm: conv needs M == B*OH*OW"; return -1; }
+    const int cin = d.K / 9;
+    a.cin_blocks = cin / BK;
+    a.OH = d.OH; a.OW = d.OW;
+    // tile = TW x TH output pixels (<= 128): maximise useful rows
+    int best_tw = 1, best_th = 1; double best_u = -1;
+    for (int tw = 1; tw <= std::min(d.OW, 128); ++tw) {
+      const int th = std::min(128 / tw, d.OH);
+      const long long tiles = static_cast<long long>((d.OW + tw - 1) / tw) * ((d.OH + th - 1) / th);
+      const double u = static_cast<double>(d.OW) * d.OH / (tiles * 128.0);
+      if (u > best_u + 1e-9) { best_u = u; best_tw = tw; best_th = th; }
+    }
+    a.TW = best_tw; a.TH = best_th;
+    a.tiles_x = (d.OW + a.TW - 1) / a.TW;
+    a.tiles_y = (d.OH + a.TH - 1) / a.TH;
+    m_tiles = d.B * a.tiles_x * a.tiles_y;
+    a.a_stage_tx = static_cast<uint32_t>(a.TW * a.TH * BK * 2);
+    if (d.a_mode == AMODE_CONV3_S1) {
+      const cuuint64_t dims[4] = {static_cast<cuuint64_t>(cin), static_cast<cuuint64_t>(d.OW),
+                                  static_cast<cuuint64_t>(d.OH), static_cast<cuuint64_t>(d.B)};
+      const cuuint64_t strides[3] = {static_cast<cuuint64_t>(d.lda) * 2, static_cast<cuuint64_t>(d.OW) * d.lda * 2,
+                                     static_cast<cuuint64_t>(d.OH) * d.OW * d.lda * 2};
+      const cuuint32_t box[4] = {BK, static_cast<cuuint32_t>(a.TW), static_cast<cuuint32_t>(a.TH), 1};
+      if (encode(&op->ta, d.dtype, 4, d.A, dims, strides, box, err)) return -1;
+    } else {
+      // input grid is (2*OH) x (2*OW); view it as [B, OH, 2, OW, (2, lda)] so that a stride-2 tap is a dense box
+      const int IWin = 2 * d.OW, IHin = 2 * d.OH;
+      const cuuint64_t dims[5] = {static_cast<cuuint64_t>(2) * d.lda, static_cast<cuuint64_t>(d.OW), 2,
+                                  static_cast<cuuint64_t>(d.OH), static_cast<cuuint64_t>(d.B)};
+      const cuuint64_t strides[4] = {static_cast<cuuint64_t>(2) * d.lda * 2, static_cast<cuuint64_t>(IWin) * d.lda * 2,
+                                     static_cast<cuuint64_t>(2) * IWin * d.lda * 2,
+                                     static_cast<cuuint64_t>(IHin) * IWin * d.lda * 2};
+      const cuuint32_t box[5] = {BK, static_cast<cuuint32_t>(a.TW), 1, static_cast<cuuint32_t>(a.TH), 1};
+      if (encode(&op->ta, d.dtype, 5, d.A, dims, strides, box, err)) return -1;
+    }
+  }
+
+  const int bn = pick_bn(d.N, m_tiles);
+  op->bn = bn;
+  a.n_tiles = (d.N + bn - 1) / bn;
+  {
+    const cuuint64_t dims[2] = {static_cast<cuuint64_t>(d.K), static_cast<cuuint64_t>(d.N)};
+    const cuuint64_t strides[1] = {static_cast<cuuint64_t>(d.K) * 2};
+    const cuuint32_t box[2] = {BK, static_cast<cuuint32_t>(bn)};
+    if (encode(&op->tb, d.dtype, 2, d.W, dims, strides, box, err)) return -1;
+  }
+  const int stage_bytes = A_STAGE_BYTES + bn * BK * 2;
+  int stages = std::max(2, (100 * 1024) / stage_bytes);
+  stages = std::min(stages, std::max(1, a.kblocks));
+  stages = std::min(stages, 6);
+  a.stages = stages;
+  op->smem = 1024 + static_cast<size_t>(stages) * stage_bytes + 256;
+  op->grid = static_cast<unsigned>(m_tiles) * a.n_tiles;
+  op->flops = 2.0 * d.M * static_cast<double>(d.N) * d.K;
+  return 0;
+}
+
+template <typename T, int BN>
+static int launch_inst(const GemmOp& op, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<T, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    attr_set = true;
+  }
+  gemm_tc_kernel<T, BN><<<op.grid, GEMM_THREADS, op.smem, st>>>(op.ta, op.tb, op.args);
+  return static_cast<int>(cudaGetLastError());
+}
+
+int gemm_launch(const GemmOp& op, cudaStream_t st) {
+#define LWB_BN_SWITCH(T)                                     \
+  switch (op.bn) {                                           \
+    case 64: return launch_inst<T, 64>(op, st);              \
+    case 128: return launch_inst<T, 128>(op, st);            \
+    case 192: return launch_inst<T, 192>(op, st);            \
+    case 256: return launch_inst<T, 256>(op, st);            \
+    default: return -1;                                      \
+  }
+  if (op.dtype == DT_BF16) { LWB_BN_SWITCH(__nv_bfloat16) } else { LWB_BN_SWITCH(__half) }
+#undef LWB_BN_SWITCH
+}
+
+}  // namespace lwb

@@ -1,0 +1,73 @@
+// tcgen05 + TMA GEMM family used for every linear / convolution of the LW-DETR forward.
+//   out[row_map(m), n] = epilogue( sum_k A[m, k] * W[n, k] )
+// A is gathered by TMA either from a plain row-major matrix, or implicitly (im2col-free) from an
+// NHWC feature map for 3x3 convolutions (stride 1 and 2).  W is always [N, K] row-major, i.e. the
+// nn.Linear / reordered conv weight layout, so both operands are K-major for the tensor core.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <string>
+
+namespace lwb {
+
+enum : int { DT_F16 = 0, DT_BF16 = 1 };
+enum : int { ACT_NONE = 0, ACT_RELU = 1, ACT_GELU = 2, ACT_SILU = 3 };
+enum : int { AMODE_PLAIN = 0, AMODE_CONV3_S1 = 1, AMODE_CONV3_S2 = 2 };
+enum : int { ROWS_PLAIN = 0, ROWS_WINDOW_MAJOR = 1 };
+
+// Device-visible arguments (passed by value to the kernel).
+struct GemmArgs {
+  int M, N, kblocks;        // valid rows / valid output columns / K in units of 64
+  int n_tiles, stages;
+  int a_mode;
+  uint32_t a_stage_tx;      // bytes TMA delivers into the A slot per stage
+  // conv geometry (output grid OH x OW per image, tile TW x TH pixels, Cin/64 channel blocks)
+  int OH, OW, TW, TH, tiles_x, tiles_y, cin_blocks, lda;
+  // epilogue
+  const float* bias;        // [N] fp32 or null
+  const float* gamma;       // [N] fp32 or null (layer-scale applied before the residual add)
+  const void* resid;        // 16-bit [*, ld_resid] or null
+  int ld_resid, resid_mod;  // residual row = m % resid_mod when resid_mod > 0
+  int act;
+  void* out;
+  int ld_out, out_fp32;
+  int rows_in;              // how input rows m are ordered: plain (b,y,x) or window-major (b,win,t)
+  int remap_rows;           // 1: write rows in spatial (b,y,x) order (needs rows_in grid IH x IW)
+  int shuffle_cout;         // >0: ConvTranspose2d(k=2,s=2) pixel shuffle, n = (dy*2+dx)*cout + co
+  int IH, IW;               // token grid per image for rows_in / shuffle (40 x 40 for the ViT)
+};
+
+// Host description of one GEMM.
+struct GemmDesc {
+  int dtype = DT_F16;
+  int a_mode = AMODE_PLAIN;
+  const void* A = nullptr;  // plain: [M, lda]; conv: NHWC [B, IH_in, IW_in, lda] (channel slice base)
+  int lda = 0;
+  int M = 0, N = 0, K = 0;  // conv: M = B*OH*OW, K = 9*Cin
+  int B = 0, OH = 0, OW = 0;  // conv output grid
+  const void* W = nullptr;  // [N, K]
+  const float* bias = nullptr;
+  const float* gamma = nullptr;
+  const void* resid = nullptr;
+  int ld_resid = 0, resid_mod = 0;
+  int act = ACT_NONE;
+  void* out = nullptr;
+  int ld_out = 0;
+  int out_fp32 = 0;
+  int rows_in = ROWS_PLAIN, remap_rows = 0, shuffle_cout = 0, IH = 0, IW = 0;
+};
+
+struct GemmOp {
+  CUtensorMap ta, tb;
+  GemmArgs args;
+  int dtype, bn;
+  unsigned grid;
+  size_t smem;
+  double flops;
+};
+
+// Returns 0 on success; on failure fills *err.
+int gemm_build(const GemmDesc& d, GemmOp* op, std::string* err);
+int gemm_launch(const GemmOp& op, cudaStream_t stream);
+
+}  // namespace lwb
