@@ -53,6 +53,99 @@ LWDETR_API int lwdetr_conv3x3(int dtype, const void* X, int ldx, int B, int OH, 
                               const void* W, int N, const float* bias, int act, void* out, int ld_out,
                               void* stream);
 
+/* LayerNorm over the last dimension of rows (vit.py:198,217 eps 1e-6; projector.py:21-47 on NHWC rows;
+ * transformer.py norms eps 1e-5).  x/y 16-bit with leading dimensions, w/b fp32 [C], C % 8 == 0, C <= 1024. */
+LWDETR_API int lwdetr_layernorm(int dtype, const void* x, int ldx, void* y, int ldy, const float* w, const float* b,
+                                float eps, int64_t rows, int C, void* stream);
+
+/* softmax(Q K^T * scale) V for `nseq` independent sequences of `seqlen` tokens and `heads` heads of
+ * width dh in {16, 32, 64}; token (s, t) is matrix row s*seqlen + t, head h occupies columns
+ * [h*dh, (h+1)*dh).  Window attention: nseq = 16*B, seqlen = 100; global: nseq = B, seqlen = 1600
+ * (vit.py:120-140, 195-222); decoder self-attention: nseq = B, seqlen = nq (attention.py:563-606). */
+LWDETR_API int lwdetr_attention(int dtype, const void* q, int ldq, const void* k, int ldk, const void* v, int ldv,
+                                void* out, int ldo, int nseq, int seqlen, int heads, int dh, float scale,
+                                void* stream);
+
+/* Multi-scale deformable attention forward.  Reference operator replaced:
+ *   MSDA.ms_deform_attn_forward(value, spatial_shapes, level_start_index, sampling_loc, attn_weight,
+ *   im2col_step) -> [B, Lq, M*D]   (models/ops/src/ms_deform_attn.h:19-35, vision.cpp:13-16,
+ *   cuda/ms_deform_attn_cuda.cu:20-80, cuda/ms_deform_im2col_cuda.cuh:237-299)
+ * fused with the softmax and sampling-location arithmetic of MSDeformAttn.forward
+ * (ops/modules/ms_deform_attn.py:118-131), so it takes the RAW projections:
+ *   value        16-bit [B, S, ldv]   (head m, channel c at column m*16 + c; D = 16)
+ *   offs_logits  16-bit [B*Lq, ld_ol] = [M*L*P*2 sampling offsets | M*L*P attention logits]
+ *   ref          fp32   [B*Lq, 4]     reference boxes (cx, cy, w, h)
+ *   spatial_shapes int32 [L, 2] (H, W) and level_start_index int32 [L] on the HOST
+ *   out          16-bit [B*Lq, ld_out]
+ * Unlike the reference there is no im2col_step batching loop and no device-side shape tensors. */
+LWDETR_API int lwdetr_msda_forward(int dtype, const void* value, int ldv, const void* offs_logits, int ld_ol,
+                                   const float* ref, void* out, int ld_out, int B, int S, int Lq, int M, int L,
+                                   int P, const int32_t* spatial_shapes_host, const int32_t* level_start_host,
+                                   void* stream);
+
+/* torch.topk(score, k, dim=1)[1] for fp32 score [B, S] -> int32 idx [B, k], sorted, ties -> lower index
+ * (transformer.py:246). */
+LWDETR_API int lwdetr_topk(const float* score, int B, int S, int k, int32_t* idx, void* stream);
+
+/* Host helper (no GPU): bicubic, align_corners=False resize of a channels-last [n_in, n_in, C] fp32 grid
+ * to [n_out, n_out, C] - the absolute position embedding resize of vit.py:26-54, done once at load. */
+LWDETR_API int lwdetr_host_bicubic(const float* src, int n_in, int C, int n_out, float* dst);
+
+/* ------------------------------------------------------------------------------------------------
+ * Model-level API: what models.lwdetr.LWDETR.forward (lwdetr.py:111-174) binds to.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct lwdetr_handle lwdetr_handle;
+
+typedef struct {
+  int32_t vit_dim, vit_depth, vit_heads;
+  int32_t window_block_mask;     /* bit i set: block i uses window attention (vit.py:195-222) */
+  int32_t n_taps, taps[4];       /* out_feature_indexes, ascending (vit.py:311-316) */
+  int32_t n_levels, level_scale_log2[2]; /* projector levels: +1 = P3 (x2), 0 = P4, -1 = P5 (/2) */
+  int32_t hidden_dim, sa_heads, ca_heads, dec_points, num_queries, dec_layers, dim_feedforward;
+  int32_t num_classes, group_detr, img_size;
+} lwdetr_config;
+
+typedef struct {
+  float* aux_logits;   /* [dec_layers-1, B, nq, num_classes] or NULL */
+  float* aux_boxes;    /* [dec_layers-1, B, nq, 4] or NULL */
+  float* enc_logits;   /* [B, nq, num_classes] or NULL */
+  float* enc_boxes;    /* [B, nq, 4] or NULL */
+  int32_t* topk_index; /* [B, nq] two-stage selection (token index per query slot) or NULL */
+} lwdetr_aux_out;
+
+/* One handle per (device, config, compute dtype); not thread-safe per handle. */
+LWDETR_API int lwdetr_create(const lwdetr_config* cfg, int dtype, lwdetr_handle** out);
+LWDETR_API void lwdetr_destroy(lwdetr_handle* h);
+
+/* Pack the checkpoint: `n` named fp32 HOST tensors with the reference's state_dict names
+ * (SURVEY.md 8b).  Folds BatchNorm into the convolutions, merges q/v biases, concatenates the
+ * deformable-attention projections, resizes the position embedding, converts to the compute dtype
+ * and uploads.  Synchronous.  May be called again after the weights change. */
+LWDETR_API int lwdetr_load_weights(lwdetr_handle* h, int n, const char* const* names, const float* const* data,
+                                   const int64_t* numel);
+
+/* images: DEVICE [B, 3, S, S], fp32 (images_fp32 = 1) or the compute dtype; outputs: DEVICE fp32
+ * pred_logits [B, nq, num_classes], pred_boxes [B, nq, 4]; aux may be NULL.  topk_override: DEVICE
+ * int32 [B, nq] or NULL - test hook that forces the two-stage selection (SURVEY.md 8c tier T2). */
+LWDETR_API int lwdetr_forward(lwdetr_handle* h, const void* images, int images_fp32, int B, float* pred_logits,
+                              float* pred_boxes, const lwdetr_aux_out* aux, const int32_t* topk_override,
+                              void* stream);
+
+/* options: "cuda_graph" (0/1) */
+LWDETR_API int lwdetr_set_option(lwdetr_handle* h, const char* name, int value);
+
+/* Debug captures (tests): after the op labelled `label` runs in the next forward, its output is copied to
+ * the HOST buffer dst as fp32 (row-major, dense).  lwdetr_capture_result returns the element count. */
+LWDETR_API int lwdetr_add_capture(lwdetr_handle* h, const char* label, float* dst, int64_t capacity);
+LWDETR_API int64_t lwdetr_capture_result(lwdetr_handle* h, int index);
+LWDETR_API void lwdetr_clear_captures(lwdetr_handle* h);
+
+/* Schedule introspection / per-op timing of the last planned batch size. */
+LWDETR_API int lwdetr_num_ops(lwdetr_handle* h);
+LWDETR_API const char* lwdetr_op_label(lwdetr_handle* h, int i);
+LWDETR_API int lwdetr_op_cost(lwdetr_handle* h, int i, double* flops, double* bytes);
+LWDETR_API int lwdetr_profile_ops(lwdetr_handle* h, int iters, float* ms_per_op, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

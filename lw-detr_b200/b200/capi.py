@@ -14,13 +14,30 @@ ACT_NONE, ACT_RELU, ACT_GELU, ACT_SILU = 0, 1, 2, 3
 
 _lib = None
 
-_vp, _i, _f = ctypes.c_void_p, ctypes.c_int, ctypes.c_float
+_vp, _i, _f, _i64 = ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_int64
 
 _SIGNATURES = {
     "lwdetr_last_error": (ctypes.c_char_p, []),
     "lwdetr_abi_version": (_i, []),
     "lwdetr_gemm": (_i, [_i, _vp, _i, _i, _i, _vp, _i, _vp, _vp, _vp, _i, _i, _i, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "lwdetr_conv3x3": (_i, [_i, _vp, _i, _i, _i, _i, _i, _i, _vp, _i, _vp, _i, _vp, _i, _vp]),
+    "lwdetr_layernorm": (_i, [_i, _vp, _i, _vp, _i, _vp, _vp, _f, _i64, _i, _vp]),
+    "lwdetr_attention": (_i, [_i, _vp, _i, _vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _i, _f, _vp]),
+    "lwdetr_msda_forward": (_i, [_i, _vp, _i, _vp, _i, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
+    "lwdetr_topk": (_i, [_vp, _i, _i, _i, _vp, _vp]),
+    "lwdetr_host_bicubic": (_i, [_vp, _i, _i, _i, _vp]),
+    "lwdetr_create": (_i, [_vp, _i, _vp]),
+    "lwdetr_destroy": (None, [_vp]),
+    "lwdetr_load_weights": (_i, [_vp, _i, _vp, _vp, _vp]),
+    "lwdetr_forward": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp]),
+    "lwdetr_set_option": (_i, [_vp, ctypes.c_char_p, _i]),
+    "lwdetr_add_capture": (_i, [_vp, ctypes.c_char_p, _vp, _i64]),
+    "lwdetr_capture_result": (_i64, [_vp, _i]),
+    "lwdetr_clear_captures": (None, [_vp]),
+    "lwdetr_num_ops": (_i, [_vp]),
+    "lwdetr_op_label": (ctypes.c_char_p, [_vp, _i]),
+    "lwdetr_op_cost": (_i, [_vp, _i, _vp, _vp]),
+    "lwdetr_profile_ops": (_i, [_vp, _i, _vp, _vp]),
 }
 
 
@@ -88,3 +105,192 @@ def conv3x3(X, Wk, out, B, OH, OW, stride, Cin, bias=None, act=ACT_NONE):
                                Wk.shape[0], ptr(bias), act, ptr(out), out.stride(0), stream_ptr()),
           "lwdetr_conv3x3")
     return out
+
+
+def layernorm(x, y, w, b, eps, rows=None, C=None):
+    rows = x.shape[0] if rows is None else rows
+    C = x.shape[1] if C is None else C
+    check(lib().lwdetr_layernorm(dtype_code(x.dtype), ptr(x), x.stride(0), ptr(y), y.stride(0), ptr(w), ptr(b), eps,
+                                 rows, C, stream_ptr()), "lwdetr_layernorm")
+    return y
+
+
+def attention(q, k, v, out, nseq, seqlen, heads, dh, scale):
+    """q/k/v/out: 2-D views [nseq*seqlen, heads*dh] (any row stride)."""
+    check(lib().lwdetr_attention(dtype_code(q.dtype), ptr(q), q.stride(0), ptr(k), k.stride(0), ptr(v), v.stride(0),
+                                 ptr(out), out.stride(0), nseq, seqlen, heads, dh, scale, stream_ptr()),
+          "lwdetr_attention")
+    return out
+
+
+def msda_forward(value, offs_logits, ref, out, B, S, Lq, M, L, P, shapes):
+    """value [B*S, ldv] view, offs_logits [B*Lq, 3*M*L*P], ref fp32 [B*Lq, 4], out [B*Lq, M*16]."""
+    sh = (ctypes.c_int32 * (2 * L))(*[v for hw in shapes for v in hw])
+    starts, acc = [], 0
+    for h, w in shapes:
+        starts.append(acc)
+        acc += h * w
+    st = (ctypes.c_int32 * L)(*starts)
+    check(lib().lwdetr_msda_forward(dtype_code(value.dtype), ptr(value), value.stride(0), ptr(offs_logits),
+                                    offs_logits.stride(0), ptr(ref), ptr(out), out.stride(0), B, S, Lq, M, L, P,
+                                    ctypes.cast(sh, _vp), ctypes.cast(st, _vp), stream_ptr()), "lwdetr_msda_forward")
+    return out
+
+
+def topk(score, k):
+    import torch
+    B, S = score.shape
+    idx = torch.empty(B, k, device=score.device, dtype=torch.int32)
+    check(lib().lwdetr_topk(ptr(score), B, S, k, ptr(idx), stream_ptr()), "lwdetr_topk")
+    return idx
+
+
+def host_bicubic(src, n_out):
+    """src: CPU fp32 [n, n, C] -> [n_out, n_out, C] (no GPU involved)."""
+    import torch
+    src = src.contiguous().float()
+    dst = torch.empty(n_out, n_out, src.shape[2], dtype=torch.float32)
+    check(lib().lwdetr_host_bicubic(ptr(src), src.shape[0], src.shape[2], n_out, ptr(dst)), "lwdetr_host_bicubic")
+    return dst
+
+
+class ConfigStruct(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_int32) for n in ("vit_dim", "vit_depth", "vit_heads", "window_block_mask", "n_taps")] + \
+               [("taps", ctypes.c_int32 * 4), ("n_levels", ctypes.c_int32), ("level_scale_log2", ctypes.c_int32 * 2)] + \
+               [(n, ctypes.c_int32) for n in ("hidden_dim", "sa_heads", "ca_heads", "dec_points", "num_queries",
+                                              "dec_layers", "dim_feedforward", "num_classes", "group_detr", "img_size")]
+
+
+class AuxOut(ctypes.Structure):
+    _fields_ = [(n, _vp) for n in ("aux_logits", "aux_boxes", "enc_logits", "enc_boxes", "topk_index")]
+
+
+def config_struct(cfg):
+    c = ConfigStruct()
+    c.vit_dim, c.vit_depth, c.vit_heads = cfg.vit_dim, cfg.vit_depth, cfg.vit_heads
+    c.window_block_mask = sum(1 << i for i in cfg.window_blocks)
+    taps = list(cfg.taps)
+    c.n_taps = len(taps)
+    for i, t in enumerate(taps):
+        c.taps[i] = t
+    c.n_levels = cfg.n_levels
+    for i, p in enumerate(cfg.projector_scale):
+        c.level_scale_log2[i] = {"P3": 1, "P4": 0, "P5": -1}[p]
+    c.hidden_dim, c.sa_heads, c.ca_heads = cfg.hidden_dim, cfg.sa_nheads, cfg.ca_nheads
+    c.dec_points, c.num_queries, c.dec_layers = cfg.dec_n_points, cfg.num_queries, cfg.dec_layers
+    c.dim_feedforward, c.num_classes, c.group_detr, c.img_size = cfg.dim_feedforward, cfg.num_classes, cfg.group_detr, cfg.img_size
+    return c
+
+
+class Engine:
+    """Owns one lwdetr_handle: packed weights + kernel schedule on the current CUDA device."""
+
+    def __init__(self, cfg, dtype):
+        import torch
+        if not torch.cuda.is_available():
+            raise RuntimeError("lwdetr_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+        self.cfg, self.dtype = cfg, dtype
+        self._h = _vp()
+        cs = config_struct(cfg)
+        check(lib().lwdetr_create(ctypes.byref(cs), dtype_code(dtype), ctypes.byref(self._h)), "lwdetr_create")
+        self._captures = []
+
+    def close(self):
+        if self._h:
+            lib().lwdetr_destroy(self._h)
+            self._h = _vp()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def load_state_dict(self, sd):
+        """sd: name -> tensor with the reference state_dict names (any device/dtype; copied to CPU fp32)."""
+        import torch
+        names, keep = [], []
+        for k, v in sd.items():
+            if not torch.is_floating_point(v):
+                continue                                    # num_batches_tracked
+            names.append(k.encode())
+            keep.append(v.detach().to("cpu", torch.float32).contiguous())
+        n = len(names)
+        c_names = (ctypes.c_char_p * n)(*names)
+        c_ptrs = (_vp * n)(*[t.data_ptr() for t in keep])
+        c_numel = (ctypes.c_int64 * n)(*[t.numel() for t in keep])
+        check(lib().lwdetr_load_weights(self._h, n, ctypes.cast(c_names, _vp), ctypes.cast(c_ptrs, _vp),
+                                        ctypes.cast(c_numel, _vp)), "lwdetr_load_weights")
+
+    def set_option(self, name, value):
+        check(lib().lwdetr_set_option(self._h, name.encode(), int(value)), "lwdetr_set_option")
+
+    def forward(self, images, want_aux=True, topk_override=None):
+        """images: CUDA [B,3,S,S] fp32 or compute dtype.  Returns the reference's output dict (fp32 CUDA tensors)."""
+        import torch
+        if images.device.type != "cuda":
+            raise RuntimeError("lwdetr_b200: images must be CUDA tensors")
+        if images.dim() != 4 or images.shape[1] != 3 or images.shape[2] != self.cfg.img_size or images.shape[3] != self.cfg.img_size:
+            raise RuntimeError("lwdetr_b200: expected images [B, 3, %d, %d], got %s" % (self.cfg.img_size, self.cfg.img_size, tuple(images.shape)))
+        if images.dtype not in (torch.float32, self.dtype):
+            images = images.float()
+        images = images.contiguous()
+        B, nq, nc, nl = images.shape[0], self.cfg.num_queries, self.cfg.num_classes, self.cfg.dec_layers
+        dev = images.device
+        logits = torch.empty(B, nq, nc, device=dev, dtype=torch.float32)
+        boxes = torch.empty(B, nq, 4, device=dev, dtype=torch.float32)
+        aux = None
+        res = {"pred_logits": logits, "pred_boxes": boxes}
+        if want_aux:
+            aux = AuxOut()
+            al = torch.empty(nl - 1, B, nq, nc, device=dev, dtype=torch.float32)
+            ab = torch.empty(nl - 1, B, nq, 4, device=dev, dtype=torch.float32)
+            el = torch.empty(B, nq, nc, device=dev, dtype=torch.float32)
+            eb = torch.empty(B, nq, 4, device=dev, dtype=torch.float32)
+            ti = torch.empty(B, nq, device=dev, dtype=torch.int32)
+            aux.aux_logits, aux.aux_boxes, aux.enc_logits, aux.enc_boxes, aux.topk_index = (
+                al.data_ptr(), ab.data_ptr(), el.data_ptr(), eb.data_ptr(), ti.data_ptr())
+            res["aux_outputs"] = [{"pred_logits": al[i], "pred_boxes": ab[i]} for i in range(nl - 1)]
+            res["enc_outputs"] = {"pred_logits": el, "pred_boxes": eb}
+            res["topk_index"] = ti
+        ov = None
+        if topk_override is not None:
+            ov = topk_override.to(device=dev, dtype=torch.int32).contiguous()
+        check(lib().lwdetr_forward(self._h, ptr(images), 1 if images.dtype == torch.float32 else 0, B, ptr(logits), ptr(boxes),
+                                   ctypes.byref(aux) if aux is not None else None, ptr(ov), stream_ptr()), "lwdetr_forward")
+        self._last_inputs = (images, ov)        # keep alive until the stream has consumed them
+        return res
+
+    # ---- debug captures -------------------------------------------------------------------------
+    def capture(self, label, numel):
+        import torch
+        t = torch.empty(int(numel), dtype=torch.float32)
+        check(lib().lwdetr_add_capture(self._h, label.encode(), ptr(t), int(numel)), "lwdetr_add_capture")
+        self._captures.append((label, t))
+        return t
+
+    def capture_results(self):
+        out = {}
+        for i, (label, t) in enumerate(self._captures):
+            n = lib().lwdetr_capture_result(self._h, i)
+            out[label] = t[:n] if n >= 0 else None
+        return out
+
+    def clear_captures(self):
+        lib().lwdetr_clear_captures(self._h)
+        self._captures = []
+
+    def ops(self):
+        n = lib().lwdetr_num_ops(self._h)
+        out = []
+        for i in range(n):
+            fl, by = ctypes.c_double(), ctypes.c_double()
+            lib().lwdetr_op_cost(self._h, i, ctypes.byref(fl), ctypes.byref(by))
+            out.append((lib().lwdetr_op_label(self._h, i).decode(), fl.value, by.value))
+        return out
+
+    def profile_ops(self, iters=10):
+        n = lib().lwdetr_num_ops(self._h)
+        ms = (ctypes.c_float * n)()
+        check(lib().lwdetr_profile_ops(self._h, iters, ctypes.cast(ms, _vp), stream_ptr()), "lwdetr_profile_ops")
+        return [(lab, fl, by, ms[i]) for i, (lab, fl, by) in enumerate(self.ops())]

@@ -1,0 +1,261 @@
+// Fused multi-head attention core: O = softmax(Q K^T * scale) V, never materialising the scores.
+// One kernel serves the three attention shapes of LW-DETR by viewing tokens as (sequence, position):
+//   * ViT window attention : 16*B sequences of 100 tokens  (vit.py:130-137 with B' = 16B)
+//   * ViT global attention : B sequences of 1600 tokens    (vit.py:201-204 + 130-137)
+//   * decoder self-attention: B sequences of nq queries    (attention.py:563-606)
+// thanks to the window-major token layout (vit.py:353-358) both ViT cases read the same [B*1600, 3C]
+// qkv matrix with no permutation.  Q/K/V are addressed as row-major matrices with a leading
+// dimension and a per-head column offset, so the packed qkv GEMM output is consumed in place.
+//
+// Round-1 implementation: flash-style online softmax, mma.sync m16n8k16 (fp32 accumulate), K/V
+// chunks double-buffered through shared memory with cp.async, exp2 on pre-scaled logits.
+#include "attn.h"
+#include "ptx.cuh"
+
+namespace lwb {
+
+template <typename T> struct Mma;
+template <> struct Mma<__half> {
+  static __device__ __forceinline__ void run(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+  }
+};
+template <> struct Mma<__nv_bfloat16> {
+  static __device__ __forceinline__ void run(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+  }
+};
+
+__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(addr));
+}
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, bool pred) {
+  const int sz = pred ? 16 : 0;   // src-size 0 => zero fill
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+static constexpr int KC = 64;   // keys per shared-memory chunk
+
+template <typename T, int DH, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) attn_kernel(const AttnArgs p) {
+  constexpr int QROWS = WARPS * 16;
+  constexpr int LDS = DH + 8;            // padded row (elements): 16 B pad => conflict-free ldmatrix
+  constexpr int CPR = DH / 8;            // 16-byte chunks per row
+  extern __shared__ __align__(16) uint8_t smem_attn[];
+  T* sQ = reinterpret_cast<T*>(smem_attn);
+  T* sK = sQ + QROWS * LDS;              // [2][KC][LDS]
+  T* sV = sK + 2 * KC * LDS;             // [2][KC][LDS]
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int qtile = blockIdx.x, head = blockIdx.y, seq = blockIdx.z;
+  const int q0 = qtile * QROWS;
+  const long long row_base = static_cast<long long>(seq) * p.seqlen;
+  const T* gq = reinterpret_cast<const T*>(p.q) + head * DH;
+  const T* gk = reinterpret_cast<const T*>(p.k) + head * DH;
+  const T* gv = reinterpret_cast<const T*>(p.v) + head * DH;
+
+  // ---- async load of the Q tile and of K/V chunk 0
+  for (int i = tid; i < QROWS * CPR; i += WARPS * 32) {
+    const int r = i / CPR, c = i % CPR;
+    const bool ok = (q0 + r) < p.seqlen;
+    const T* src = gq + (row_base + (ok ? q0 + r : 0)) * p.ldq + c * 8;
+    cp_async16(smem_u32(sQ + r * LDS + c * 8), src, ok);
+  }
+  auto load_kv = [&](int chunk, int buf) {
+    const int k0 = chunk * KC;
+    for (int i = tid; i < KC * CPR; i += WARPS * 32) {
+      const int r = i / CPR, c = i % CPR;
+      const bool ok = (k0 + r) < p.seqlen;
+      const long long row = row_base + (ok ? k0 + r : 0);
+      cp_async16(smem_u32(sK + (buf * KC + r) * LDS + c * 8), gk + row * p.ldk + c * 8, ok);
+      cp_async16(smem_u32(sV + (buf * KC + r) * LDS + c * 8), gv + row * p.ldv + c * 8, ok);
+    }
+  };
+  const int nchunks = (p.seqlen + KC - 1) / KC;
+  load_kv(0, 0);
+  cp_async_commit();
+
+  uint32_t qf[DH / 16][4];
+  float o[DH / 8][4];
+#pragma unroll
+  for (int i = 0; i < DH / 8; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
+  float m_run[2] = {-INFINITY, -INFINITY}, l_run[2] = {0.f, 0.f};
+  const int g = lane >> 2, t4 = lane & 3;
+
+  for (int ch = 0; ch < nchunks; ++ch) {
+    const int buf = ch & 1;
+    if (ch + 1 < nchunks) {
+      load_kv(ch + 1, buf ^ 1);
+      cp_async_commit();
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncthreads();
+    if (ch == 0) {
+      // Q fragments (A operand): ldmatrix x4 = (rows 0-7,k 0-7), (rows 8-15,k 0-7), (rows 0-7,k 8-15), (rows 8-15,k 8-15)
+#pragma unroll
+      for (int kk = 0; kk < DH / 16; ++kk) {
+        const int r = warp * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
+        const int c = kk * 16 + (lane >> 4) * 8;
+        ldsm_x4(qf[kk], smem_u32(sQ + r * LDS + c));
+      }
+    }
+    const T* cK = sK + buf * KC * LDS;
+    const T* cV = sV + buf * KC * LDS;
+
+    // ---- S = Q K^T for 64 keys: 8 n-tiles of 8 keys
+    float s[KC / 8][4];
+#pragma unroll
+    for (int nt = 0; nt < KC / 8; ++nt) s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
+#pragma unroll
+    for (int nt = 0; nt < KC / 8; nt += 2) {
+#pragma unroll
+      for (int kk = 0; kk < DH / 16; ++kk) {
+        // x4 = (keys nt*8.., dh lo), (keys nt*8.., dh hi), (keys (nt+1)*8.., dh lo), (keys (nt+1)*8.., dh hi)
+        uint32_t kf[4];
+        const int key = (nt + (lane >> 4)) * 8 + (lane & 7);
+        const int c = kk * 16 + ((lane >> 3) & 1) * 8;
+        ldsm_x4(kf, smem_u32(cK + key * LDS + c));
+        Mma<T>::run(s[nt], qf[kk], kf[0], kf[1]);
+        Mma<T>::run(s[nt + 1], qf[kk], kf[2], kf[3]);
+      }
+    }
+    // ---- scale, mask the tail keys, online softmax
+    const int kbase = ch * KC;
+    float mx[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+    for (int nt = 0; nt < KC / 8; ++nt) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int key = kbase + nt * 8 + t4 * 2 + (j & 1);
+        const float v = key < p.seqlen ? s[nt][j] * p.scale_log2 : -INFINITY;
+        s[nt][j] = v;
+        mx[j >> 1] = fmaxf(mx[j >> 1], v);
+      }
+    }
+    float alpha[2], rs[2] = {0.f, 0.f};
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      mx[h] = fmaxf(mx[h], __shfl_xor_sync(0xffffffffu, mx[h], 1));
+      mx[h] = fmaxf(mx[h], __shfl_xor_sync(0xffffffffu, mx[h], 2));
+      const float m_new = fmaxf(m_run[h], mx[h]);
+      alpha[h] = fast_exp2(m_run[h] - m_new);
+      m_run[h] = m_new;
+    }
+    uint32_t pf[KC / 16][4];
+#pragma unroll
+    for (int nt = 0; nt < KC / 8; ++nt) {
+      const float p0 = fast_exp2(s[nt][0] - m_run[0]);
+      const float p1 = fast_exp2(s[nt][1] - m_run[0]);
+      const float p2 = fast_exp2(s[nt][2] - m_run[1]);
+      const float p3 = fast_exp2(s[nt][3] - m_run[1]);
+      rs[0] += p0 + p1;
+      rs[1] += p2 + p3;
+      // C fragments of n-tiles (2j, 2j+1) form the A fragment of key-step j
+      pf[nt >> 1][(nt & 1) * 2 + 0] = Cvt<T>::pack(p0, p1);
+      pf[nt >> 1][(nt & 1) * 2 + 1] = Cvt<T>::pack(p2, p3);
+    }
+#pragma unroll
+    for (int h = 0; h < 2; ++h) l_run[h] = l_run[h] * alpha[h] + rs[h];
+#pragma unroll
+    for (int dt = 0; dt < DH / 8; ++dt) {
+      o[dt][0] *= alpha[0];
+      o[dt][1] *= alpha[0];
+      o[dt][2] *= alpha[1];
+      o[dt][3] *= alpha[1];
+    }
+    // ---- O += P V
+#pragma unroll
+    for (int kt = 0; kt < KC / 16; ++kt) {
+#pragma unroll
+      for (int dt = 0; dt < DH / 8; dt += 2) {
+        // trans x4 = (keys 0-7, dh dt), (keys 8-15, dh dt), (keys 0-7, dh dt+1), (keys 8-15, dh dt+1)
+        uint32_t vf[4];
+        const int key = kt * 16 + (lane & 15);
+        const int c = (dt + (lane >> 4)) * 8;
+        ldsm_x4_t(vf, smem_u32(cV + key * LDS + c));
+        Mma<T>::run(o[dt], pf[kt], vf[0], vf[1]);
+        Mma<T>::run(o[dt + 1], pf[kt], vf[2], vf[3]);
+      }
+    }
+    __syncthreads();   // everyone is done with this buffer before it is refilled
+  }
+
+  // ---- finalise: divide by the row sums, stage through this warp's Q rows, 16-byte coalesced stores
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    l_run[h] += __shfl_xor_sync(0xffffffffu, l_run[h], 1);
+    l_run[h] += __shfl_xor_sync(0xffffffffu, l_run[h], 2);
+    l_run[h] = 1.f / l_run[h];
+  }
+  T* sO = sQ + warp * 16 * LDS;
+#pragma unroll
+  for (int dt = 0; dt < DH / 8; ++dt) {
+    *reinterpret_cast<uint32_t*>(sO + g * LDS + dt * 8 + t4 * 2) = Cvt<T>::pack(o[dt][0] * l_run[0], o[dt][1] * l_run[0]);
+    *reinterpret_cast<uint32_t*>(sO + (g + 8) * LDS + dt * 8 + t4 * 2) =
+        Cvt<T>::pack(o[dt][2] * l_run[1], o[dt][3] * l_run[1]);
+  }
+  __syncwarp();
+  T* go = reinterpret_cast<T*>(p.o) + head * DH;
+  for (int i = lane; i < 16 * CPR; i += 32) {
+    const int r = i / CPR, c = i % CPR;
+    const int qrow = q0 + warp * 16 + r;
+    if (qrow < p.seqlen)
+      *reinterpret_cast<U4*>(go + (row_base + qrow) * p.ldo + c * 8) = *reinterpret_cast<const U4*>(sO + r * LDS + c * 8);
+  }
+}
+
+template <typename T, int DH, int WARPS>
+static int launch(const AttnArgs& a, cudaStream_t st) {
+  constexpr int LDS = DH + 8;
+  const size_t smem = static_cast<size_t>(WARPS * 16 + 4 * KC) * LDS * sizeof(T);
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(attn_kernel<T, DH, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    attr = true;
+  }
+  dim3 grid((a.seqlen + WARPS * 16 - 1) / (WARPS * 16), a.heads, a.nseq);
+  attn_kernel<T, DH, WARPS><<<grid, WARPS * 32, smem, st>>>(a);
+  return static_cast<int>(cudaGetLastError());
+}
+
+template <typename T>
+static int dispatch(const AttnArgs& a, int dh, cudaStream_t st) {
+  const int warps = a.seqlen <= 112 ? 7 : (a.seqlen >= 1024 ? 8 : 4);
+#define LWB_ATTN_CASE(D, W) if (dh == D && warps == W) return launch<T, D, W>(a, st);
+  LWB_ATTN_CASE(16, 7) LWB_ATTN_CASE(16, 8) LWB_ATTN_CASE(16, 4)
+  LWB_ATTN_CASE(32, 7) LWB_ATTN_CASE(32, 8) LWB_ATTN_CASE(32, 4)
+  LWB_ATTN_CASE(64, 7) LWB_ATTN_CASE(64, 8) LWB_ATTN_CASE(64, 4)
+#undef LWB_ATTN_CASE
+  return -2;
+}
+
+int attention_launch(int dtype, const AttnArgs& a, int dh, cudaStream_t st) {
+  return dtype == DT_BF16 ? dispatch<__nv_bfloat16>(a, dh, st) : dispatch<__half>(a, dh, st);
+}
+
+}  // namespace lwb

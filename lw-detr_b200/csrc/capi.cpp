@@ -5,7 +5,15 @@
 
 #include <string>
 
+#include <map>
+#include <new>
+#include <vector>
+
+#include "attn.h"
+#include "engine.h"
 #include "gemm_tc.h"
+#include "msda.h"
+#include "rowops.h"
 
 namespace {
 thread_local std::string g_err;
@@ -54,6 +62,141 @@ int lwdetr_conv3x3(int dtype, const void* X, int ldx, int B, int OH, int OW, int
   if (lwb::gemm_build(d, &op, &err)) return fail("lwdetr_conv3x3: " + err);
   int e = lwb::gemm_launch(op, static_cast<cudaStream_t>(stream));
   if (e) return cuda_fail(e, "lwdetr_conv3x3 launch");
+  return 0;
+}
+
+
+int lwdetr_layernorm(int dtype, const void* x, int ldx, void* y, int ldy, const float* w, const float* b, float eps,
+                     int64_t rows, int C, void* stream) {
+  if (!x || !y || !w || !b) return fail("lwdetr_layernorm: null pointer");
+  lwb::LayerNormArgs a{};
+  a.x = x; a.ldx = ldx; a.y = y; a.ldy = ldy; a.w = w; a.b = b; a.eps = eps; a.rows = rows; a.C = C; a.flag_mod = 1;
+  int e = lwb::layernorm_launch(dtype, a, static_cast<cudaStream_t>(stream));
+  if (e == -2) return fail("lwdetr_layernorm: C must be a multiple of 8 and <= 1024");
+  if (e) return cuda_fail(e, "lwdetr_layernorm launch");
+  return 0;
+}
+
+int lwdetr_attention(int dtype, const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, void* out, int ldo,
+                     int nseq, int seqlen, int heads, int dh, float scale, void* stream) {
+  if (!q || !k || !v || !out) return fail("lwdetr_attention: null pointer");
+  if ((ldq | ldk | ldv | ldo) % 8) return fail("lwdetr_attention: leading dimensions must be multiples of 8");
+  lwb::AttnArgs a{};
+  a.q = q; a.k = k; a.v = v; a.ldq = ldq; a.ldk = ldk; a.ldv = ldv; a.o = out; a.ldo = ldo; a.seqlen = seqlen; a.nseq = nseq;
+  a.heads = heads; a.scale_log2 = scale * 1.4426950408889634f;
+  int e = lwb::attention_launch(dtype, a, dh, static_cast<cudaStream_t>(stream));
+  if (e == -2) return fail("lwdetr_attention: head dim must be 16, 32 or 64");
+  if (e) return cuda_fail(e, "lwdetr_attention launch");
+  return 0;
+}
+
+int lwdetr_msda_forward(int dtype, const void* value, int ldv, const void* offs_logits, int ld_ol, const float* ref, void* out,
+                        int ld_out, int B, int S, int Lq, int M, int L, int P, const int32_t* spatial_shapes_host,
+                        const int32_t* level_start_host, void* stream) {
+  if (!value || !offs_logits || !ref || !out || !spatial_shapes_host || !level_start_host) return fail("lwdetr_msda_forward: null pointer");
+  if (L < 1 || L > lwb::MSDA_MAX_LEVELS) return fail("lwdetr_msda_forward: 1..4 levels supported");
+  if ((ldv % 8) || (ld_out % 8) || (ld_ol % 2)) return fail("lwdetr_msda_forward: misaligned leading dimension");
+  lwb::MsdaArgs a{};
+  a.value = value; a.ldv = ldv; a.offs_logits = offs_logits; a.ld_ol = ld_ol; a.ref = ref; a.out = out; a.ld_out = ld_out;
+  a.batch = B; a.nq = Lq; a.heads = M; a.levels = L; a.points = P; a.S = S;
+  for (int l = 0; l < L; ++l) { a.lvl_h[l] = spatial_shapes_host[2 * l]; a.lvl_w[l] = spatial_shapes_host[2 * l + 1]; a.lvl_start[l] = level_start_host[l]; }
+  int e = lwb::msda_launch(dtype, a, static_cast<cudaStream_t>(stream));
+  if (e == -2) return fail("lwdetr_msda_forward: unsupported (levels, points) combination");
+  if (e) return cuda_fail(e, "lwdetr_msda_forward launch");
+  return 0;
+}
+
+int lwdetr_topk(const float* score, int B, int S, int k, int32_t* idx, void* stream) {
+  if (!score || !idx) return fail("lwdetr_topk: null pointer");
+  int e = lwb::topk_launch(score, B, S, k, idx, static_cast<cudaStream_t>(stream));
+  if (e == -2) return fail("lwdetr_topk: need k <= S <= 16384");
+  if (e) return cuda_fail(e, "lwdetr_topk launch");
+  return 0;
+}
+
+int lwdetr_host_bicubic(const float* src, int n_in, int C, int n_out, float* dst) {
+  if (!src || !dst || n_in < 1 || n_out < 1 || C < 1) return fail("lwdetr_host_bicubic: bad arguments");
+  lwb::bicubic_resize_chlast(src, n_in, C, n_out, dst);
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------ model level
+struct lwdetr_handle {
+  lwb::Engine* eng;
+};
+
+int lwdetr_create(const lwdetr_config* cfg, int dtype, lwdetr_handle** out) {
+  if (!cfg || !out) return fail("lwdetr_create: null pointer");
+  if (dtype != LWDETR_F16 && dtype != LWDETR_BF16) return fail("lwdetr_create: dtype must be LWDETR_F16 or LWDETR_BF16");
+  if (cfg->n_taps < 1 || cfg->n_taps > 4 || cfg->n_levels < 1 || cfg->n_levels > 2 || cfg->vit_depth < 1 || cfg->vit_depth > 31)
+    return fail("lwdetr_create: unsupported configuration");
+  if (cfg->img_size % 64 != 0 || cfg->vit_dim % 64 != 0 || cfg->hidden_dim % 128 != 0)
+    return fail("lwdetr_create: img_size % 64, vit_dim % 64 and hidden_dim % 128 must be 0");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail("lwdetr_create: no CUDA device (there is no CPU fallback)");
+  lwdetr_handle* h = new (std::nothrow) lwdetr_handle;
+  if (!h) return fail("lwdetr_create: out of memory");
+  h->eng = new (std::nothrow) lwb::Engine(*cfg, dtype);
+  if (!h->eng) { delete h; return fail("lwdetr_create: out of memory"); }
+  *out = h;
+  return 0;
+}
+
+void lwdetr_destroy(lwdetr_handle* h) {
+  if (!h) return;
+  delete h->eng;
+  delete h;
+}
+
+int lwdetr_load_weights(lwdetr_handle* h, int n, const char* const* names, const float* const* data, const int64_t* numel) {
+  if (!h || !names || !data || !numel) return fail("lwdetr_load_weights: null pointer");
+  std::map<std::string, lwb::HostTensor> m;
+  for (int i = 0; i < n; ++i) m[names[i]] = lwb::HostTensor{data[i], numel[i]};
+  std::string err;
+  if (h->eng->load_weights(m, &err)) return fail("lwdetr_load_weights: " + err);
+  return 0;
+}
+
+int lwdetr_forward(lwdetr_handle* h, const void* images, int images_fp32, int B, float* pred_logits, float* pred_boxes,
+                   const lwdetr_aux_out* aux, const int32_t* topk_override, void* stream) {
+  if (!h || !images) return fail("lwdetr_forward: null pointer");
+  std::string err;
+  if (h->eng->forward(images, images_fp32, B, pred_logits, pred_boxes, aux, topk_override, static_cast<cudaStream_t>(stream), &err))
+    return fail(err);
+  return 0;
+}
+
+int lwdetr_set_option(lwdetr_handle* h, const char* name, int value) {
+  if (!h || !name) return fail("lwdetr_set_option: null pointer");
+  if (h->eng->set_option(name, value)) return fail(std::string("lwdetr_set_option: unknown option ") + name);
+  return 0;
+}
+
+int lwdetr_add_capture(lwdetr_handle* h, const char* label, float* dst, int64_t capacity) {
+  if (!h || !label || !dst) return fail("lwdetr_add_capture: null pointer");
+  h->eng->add_capture(label, dst, capacity);
+  return 0;
+}
+int64_t lwdetr_capture_result(lwdetr_handle* h, int index) { return h ? h->eng->capture_written(index) : -1; }
+void lwdetr_clear_captures(lwdetr_handle* h) { if (h) h->eng->clear_captures(); }
+
+int lwdetr_num_ops(lwdetr_handle* h) { return h ? h->eng->num_ops() : 0; }
+const char* lwdetr_op_label(lwdetr_handle* h, int i) {
+  if (!h || i < 0 || i >= h->eng->num_ops()) return "";
+  return h->eng->op(i).label.c_str();
+}
+int lwdetr_op_cost(lwdetr_handle* h, int i, double* flops, double* bytes) {
+  if (!h || i < 0 || i >= h->eng->num_ops()) return fail("lwdetr_op_cost: bad index");
+  if (flops) *flops = h->eng->op(i).flops;
+  if (bytes) *bytes = h->eng->op(i).bytes;
+  return 0;
+}
+int lwdetr_profile_ops(lwdetr_handle* h, int iters, float* ms_per_op, void* stream) {
+  if (!h || !ms_per_op || iters < 1) return fail("lwdetr_profile_ops: bad arguments");
+  std::vector<float> ms;
+  std::string err;
+  if (h->eng->profile_ops(iters, &ms, static_cast<cudaStream_t>(stream), &err)) return fail(err);
+  for (size_t i = 0; i < ms.size(); ++i) ms_per_op[i] = ms[i];
   return 0;
 }
 

@@ -1,0 +1,97 @@
+// LW-DETR forward engine: weight packing (folding, layout changes, 16-bit conversion) and the fixed
+// kernel schedule for one batch size.  Host-only interface; see engine.cpp.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <functional>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "lwdetr_b200.h"
+
+namespace lwb {
+
+struct HostTensor {
+  const float* data;
+  long long numel;
+};
+
+struct Capture {
+  std::string label;
+  float* dst;
+  long long capacity;   // in floats
+  long long written;    // rows*cols actually written (or -1 if label not found)
+};
+
+struct Op {
+  std::string label;
+  std::function<int(cudaStream_t)> run;
+  // output description for debug captures
+  const void* out = nullptr;
+  long long rows = 0;
+  int cols = 0, ld = 0, fp32 = 0;
+  double flops = 0, bytes = 0;
+};
+
+class Engine {
+ public:
+  Engine(const lwdetr_config& cfg, int dtype);
+  ~Engine();
+  int load_weights(const std::map<std::string, HostTensor>& w, std::string* err);
+  int forward(const void* images, int images_fp32, int B, float* pred_logits, float* pred_boxes,
+              const lwdetr_aux_out* aux, const int32_t* topk_override, cudaStream_t st, std::string* err);
+  void add_capture(const char* label, float* dst, long long cap) { captures_.push_back({label, dst, cap, -1}); }
+  void clear_captures() { captures_.clear(); }
+  long long capture_written(int i) const { return i < (int)captures_.size() ? captures_[i].written : -1; }
+  int set_option(const char* name, int value);
+  int num_ops() const { return static_cast<int>(ops_.size()); }
+  const Op& op(int i) const { return ops_[i]; }
+  const lwdetr_config& config() const { return cfg_; }
+  // per-op timing of the last planned batch (CUDA events, `iters` runs per op); returns ms per op
+  int profile_ops(int iters, std::vector<float>* ms, cudaStream_t st, std::string* err);
+
+ private:
+  struct DevBuf { void* p = nullptr; size_t bytes = 0; };
+  int plan(int B, std::string* err);
+  void* walloc(size_t bytes);      // weight arena (bump)
+  void* salloc(size_t bytes);      // workspace arena (bump)
+  void* upload16(const std::vector<float>& v);
+  float* upload32(const std::vector<float>& v);
+  int do_capture(const Op& op, cudaStream_t st);
+
+  lwdetr_config cfg_;
+  int dtype_;
+  int planned_B_ = 0;
+  bool weights_loaded_ = false;
+  int use_graph_ = 0;
+  cudaGraphExec_t graph_exec_ = nullptr;
+  const void* graph_images_ = nullptr;
+  const int32_t* graph_topk_ = nullptr;
+  int graph_images_fp32_ = -1;
+  std::vector<Op> ops_;
+  std::vector<Capture> captures_;
+  // arenas
+  DevBuf warena_, sarena_;
+  size_t woff_ = 0, soff_ = 0;
+  // packed weights (device pointers), keyed by short names
+  std::map<std::string, void*> W_;
+  std::map<std::string, float*> F_;
+  std::vector<uint8_t> invalid_rows_;   // per memory token
+  // live I/O pointers patched into the schedule at forward() time
+  const void* in_images_ = nullptr;
+  int in_images_fp32_ = 1;
+  const int32_t* in_topk_override_ = nullptr;
+  // result buffers (engine owned)
+  float* out_logits_ = nullptr;   // [layers, B, nq, 96]
+  float* out_boxes_ = nullptr;    // [layers, B, nq, 4]
+  float* out_enc_logits_ = nullptr;  // [B, nq, ncls]
+  float* out_enc_boxes_ = nullptr;   // [B, nq, 4]
+  int* topk_idx_ = nullptr;          // [B, nq]
+};
+
+// host helpers exposed for CPU tests
+void bicubic_resize_chlast(const float* src, int n_in, int C, int n_out, float* dst);   // [n_in,n_in,C] -> [n_out,n_out,C]
+
+}  // namespace lwb

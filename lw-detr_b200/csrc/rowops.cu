@@ -1,0 +1,378 @@
+// Memory-bound helper kernels of the LW-DETR forward: LayerNorm, patch gathering, row max, per-image
+// top-k, gathers, box re-parameterisation and the sine query embedding.  All are HBM-bound; they use
+// 16/32-byte accesses, one warp per row where a row reduction is needed, and fp32 math throughout.
+#include "rowops.h"
+#include "ptx.cuh"
+
+#include <math_constants.h>
+
+namespace lwb {
+
+// ----------------------------------------------------------------------------------- LayerNorm
+// y = (x - mean) / sqrt(var + eps) * w + b per row (biased variance), one warp per row, row in
+// registers.  Serves nn.LayerNorm in the ViT (eps 1e-6, vit.py:198,217), the channel-first
+// LayerNorm of the projector on NHWC rows (projector.py:21-47) and the decoder norms (eps 1e-5).
+// Optional: rows flagged in `row_flag` take `override_vec` as input (masked two-stage memory rows,
+// transformer.py:116-123); optional second output y2 = y + add_src (decoder: tgt + query_pos).
+template <typename T, int CHUNKS>   // CHUNKS = ceil(C / 256): 8-element chunks per lane
+__global__ void __launch_bounds__(256) layernorm_kernel(const LayerNormArgs p) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long row = static_cast<long long>(blockIdx.x) * 8 + warp;
+  if (row >= p.rows) return;
+  const int nchunk = p.C >> 3;
+  float v[CHUNKS][8];
+  const bool ovr = p.row_flag != nullptr && p.row_flag[row % p.flag_mod] != 0;
+  const T* x = reinterpret_cast<const T*>(p.x) + row * p.ldx;
+#pragma unroll
+  for (int i = 0; i < CHUNKS; ++i) {
+    const int c = lane + i * 32;
+    if (c < nchunk) {
+      if (ovr) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[i][j] = p.override_vec[c * 8 + j];
+      } else {
+        const U4 u = *reinterpret_cast<const U4*>(x + c * 8);
+        const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 f = Cvt<T>::unpack(w4[j]);
+          v[i][2 * j] = f.x;
+          v[i][2 * j + 1] = f.y;
+        }
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[i][j] = 0.f;
+    }
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < CHUNKS; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s += v[i][j];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float mean = s / p.C;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < CHUNKS; ++i) {
+    if (lane + i * 32 < nchunk) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float d = v[i][j] - mean;
+        q += d * d;
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+  const float rstd = rsqrtf(q / p.C + p.eps);
+  const long long yrow = p.y_group > 0 ? (row / p.y_group) * p.y_group_stride + p.y_row_off + row % p.y_group : row;
+  T* y = reinterpret_cast<T*>(p.y) + yrow * p.ldy;
+#pragma unroll
+  for (int i = 0; i < CHUNKS; ++i) {
+    const int c = lane + i * 32;
+    if (c < nchunk) {
+      float r[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) r[j] = (v[i][j] - mean) * rstd * __ldg(p.w + c * 8 + j) + __ldg(p.b + c * 8 + j);
+      U4 o;
+      o.x = Cvt<T>::pack(r[0], r[1]); o.y = Cvt<T>::pack(r[2], r[3]);
+      o.z = Cvt<T>::pack(r[4], r[5]); o.w = Cvt<T>::pack(r[6], r[7]);
+      *reinterpret_cast<U4*>(y + c * 8) = o;
+      if (p.y2 != nullptr) {
+        const T* a = reinterpret_cast<const T*>(p.add_src) + row * p.ld_add + c * 8;
+        const U4 u = *reinterpret_cast<const U4*>(a);
+        const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
+        uint32_t o2[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 f = Cvt<T>::unpack(w4[j]);
+          // add to the ROUNDED y so that y2 == y + add exactly as a 16-bit consumer would compute it
+          const float2 yr = Cvt<T>::unpack(j == 0 ? o.x : j == 1 ? o.y : j == 2 ? o.z : o.w);
+          o2[j] = Cvt<T>::pack(yr.x + f.x, yr.y + f.y);
+        }
+        U4 oo; oo.x = o2[0]; oo.y = o2[1]; oo.z = o2[2]; oo.w = o2[3];
+        *reinterpret_cast<U4*>(reinterpret_cast<T*>(p.y2) + row * p.ldy2 + c * 8) = oo;
+      }
+    }
+  }
+}
+
+template <typename T>
+static int ln_dispatch(const LayerNormArgs& a, cudaStream_t st) {
+  const unsigned grid = static_cast<unsigned>((a.rows + 7) / 8);
+  const int chunks = (a.C + 255) / 256;
+  if (chunks == 1) layernorm_kernel<T, 1><<<grid, 256, 0, st>>>(a);
+  else if (chunks == 2) layernorm_kernel<T, 2><<<grid, 256, 0, st>>>(a);
+  else if (chunks == 3) layernorm_kernel<T, 3><<<grid, 256, 0, st>>>(a);
+  else if (chunks == 4) layernorm_kernel<T, 4><<<grid, 256, 0, st>>>(a);
+  else return -2;
+  return static_cast<int>(cudaGetLastError());
+}
+int layernorm_launch(int dtype, const LayerNormArgs& a, cudaStream_t st) {
+  if (a.C % 8 != 0 || a.C > 1024) return -2;
+  return dtype == DT_BF16 ? ln_dispatch<__nv_bfloat16>(a, st) : ln_dispatch<__half>(a, st);
+}
+
+// ----------------------------------------------------------------------------------- patch gather
+// Image [B,3,S,S] (fp32 or 16-bit, NCHW) -> A [B*G*G, 3*256] 16-bit with rows in WINDOW-MAJOR token
+// order and k = c*256 + py*16 + px, so that the 16x16/s16 patch-embedding conv (vit.py:79-83)
+// becomes one tcgen05 GEMM whose output is already in the layout of vit.py:353-358.
+template <typename T, typename TIn>
+__global__ void __launch_bounds__(256) patch_gather_kernel(const TIn* __restrict__ img, T* __restrict__ A, int B, int S) {
+  const int G = S / 16, T_ = G * G;
+  const long long total = static_cast<long long>(B) * T_ * 48;      // (row, c, py)
+  const long long id = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (id >= total) return;
+  const long long rows = static_cast<long long>(B) * T_;
+  const long long r = id % rows;
+  const int cp = static_cast<int>(id / rows);
+  const int c = cp / 16, py = cp % 16;
+  const int b = static_cast<int>(r / T_), rem = static_cast<int>(r % T_);
+  const int wh = G / 4, wsz = wh * wh;
+  const int win = rem / wsz, t = rem % wsz;
+  const int Y = (win >> 2) * wh + t / wh, X = (win & 3) * wh + t % wh;
+  const TIn* src = img + ((static_cast<long long>(b) * 3 + c) * S + (Y * 16 + py)) * S + X * 16;
+  float f[16];
+  if constexpr (sizeof(TIn) == 4) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float4 q = __ldg(reinterpret_cast<const float4*>(src) + j);
+      f[4 * j] = q.x; f[4 * j + 1] = q.y; f[4 * j + 2] = q.z; f[4 * j + 3] = q.w;
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) f[j] = Cvt<T>::to_f(reinterpret_cast<const T*>(src)[j]);
+  }
+  U8 o;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) o.v[j] = Cvt<T>::pack(f[2 * j], f[2 * j + 1]);
+  stg256(A + r * 768 + c * 256 + py * 16, o);
+}
+
+int patch_gather_launch(int dtype, const void* img, int img_is_fp32, void* A, int B, int S, cudaStream_t st) {
+  if (S % 64 != 0) return -2;
+  const long long total = static_cast<long long>(B) * (S / 16) * (S / 16) * 48;
+  const unsigned grid = static_cast<unsigned>((total + 255) / 256);
+  if (dtype == DT_BF16) {
+    if (img_is_fp32) patch_gather_kernel<__nv_bfloat16, float><<<grid, 256, 0, st>>>(static_cast<const float*>(img), static_cast<__nv_bfloat16*>(A), B, S);
+    else patch_gather_kernel<__nv_bfloat16, __nv_bfloat16><<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(img), static_cast<__nv_bfloat16*>(A), B, S);
+  } else {
+    if (img_is_fp32) patch_gather_kernel<__half, float><<<grid, 256, 0, st>>>(static_cast<const float*>(img), static_cast<__half*>(A), B, S);
+    else patch_gather_kernel<__half, __half><<<grid, 256, 0, st>>>(static_cast<const __half*>(img), static_cast<__half*>(A), B, S);
+  }
+  return static_cast<int>(cudaGetLastError());
+}
+
+// ----------------------------------------------------------------------------------- window-major -> spatial copy
+template <typename T>
+__global__ void __launch_bounds__(256) unwindow_kernel(const T* __restrict__ src, int lds, T* __restrict__ dst, int ldd,
+                                                       long long rows, int C, int G) {
+  const int cpr = C / 8;
+  const long long id = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (id >= rows * cpr) return;
+  const long long r = id / cpr;
+  const int c = static_cast<int>(id % cpr);
+  const int T_ = G * G, wh = G / 4, wsz = wh * wh;
+  const long long b = r / T_;
+  const int rem = static_cast<int>(r % T_);
+  const int win = rem / wsz, t = rem % wsz;
+  const int y = (win >> 2) * wh + t / wh, x = (win & 3) * wh + t % wh;
+  const U4 v = *reinterpret_cast<const U4*>(src + r * lds + c * 8);
+  *reinterpret_cast<U4*>(dst + (b * T_ + y * G + x) * ldd + c * 8) = v;
+}
+int unwindow_launch(int dtype, const void* src, int lds, void* dst, int ldd, long long rows, int C, int G, cudaStream_t st) {
+  const long long n = rows * (C / 8);
+  const unsigned grid = static_cast<unsigned>((n + 255) / 256);
+  if (dtype == DT_BF16) unwindow_kernel<<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(src), lds, static_cast<__nv_bfloat16*>(dst), ldd, rows, C, G);
+  else unwindow_kernel<<<grid, 256, 0, st>>>(static_cast<const __half*>(src), lds, static_cast<__half*>(dst), ldd, rows, C, G);
+  return static_cast<int>(cudaGetLastError());
+}
+
+// ----------------------------------------------------------------------------------- out = a[r % amod] + b[r]
+template <typename T>
+__global__ void __launch_bounds__(256) add_rows_kernel(const T* __restrict__ a, int lda, long long amod, const T* __restrict__ b,
+                                                       int ldb, T* __restrict__ out, int ldo, long long rows, int C) {
+  const int cpr = C / 8;
+  const long long id = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (id >= rows * cpr) return;
+  const long long r = id / cpr;
+  const int c = static_cast<int>(id % cpr) * 8;
+  const U4 ua = *reinterpret_cast<const U4*>(a + (amod > 0 ? r % amod : r) * lda + c);
+  uint32_t wa[4] = {ua.x, ua.y, ua.z, ua.w}, wb[4] = {0, 0, 0, 0};
+  if (b != nullptr) {
+    const U4 ub = *reinterpret_cast<const U4*>(b + r * ldb + c);
+    wb[0] = ub.x; wb[1] = ub.y; wb[2] = ub.z; wb[3] = ub.w;
+  }
+  uint32_t o[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float2 fa = Cvt<T>::unpack(wa[j]);
+    float2 fb = make_float2(0.f, 0.f);
+    if (b != nullptr) fb = Cvt<T>::unpack(wb[j]);
+    o[j] = Cvt<T>::pack(fa.x + fb.x, fa.y + fb.y);
+  }
+  U4 oo; oo.x = o[0]; oo.y = o[1]; oo.z = o[2]; oo.w = o[3];
+  *reinterpret_cast<U4*>(out + r * ldo + c) = oo;
+}
+int add_rows_launch(int dtype, const void* a, int lda, long long amod, const void* b, int ldb, void* out, int ldo,
+                    long long rows, int C, cudaStream_t st) {
+  const long long n = rows * (C / 8);
+  const unsigned grid = static_cast<unsigned>((n + 255) / 256);
+  if (dtype == DT_BF16) add_rows_kernel<<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(a), lda, amod, static_cast<const __nv_bfloat16*>(b), ldb, static_cast<__nv_bfloat16*>(out), ldo, rows, C);
+  else add_rows_kernel<<<grid, 256, 0, st>>>(static_cast<const __half*>(a), lda, amod, static_cast<const __half*>(b), ldb, static_cast<__half*>(out), ldo, rows, C);
+  return static_cast<int>(cudaGetLastError());
+}
+
+// ----------------------------------------------------------------------------------- row max over classes (fp32)
+__global__ void __launch_bounds__(256) rowmax_kernel(const float* __restrict__ x, int ld, int n, float* __restrict__ out, long long rows) {
+  const long long row = static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  float m = -CUDART_INF_F;
+  for (int i = lane; i < n; i += 32) m = fmaxf(m, x[row * ld + i]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if (lane == 0) out[row] = m;
+}
+int rowmax_launch(const float* x, int ld, int n, float* out, long long rows, cudaStream_t st) {
+  rowmax_kernel<<<static_cast<unsigned>((rows + 7) / 8), 256, 0, st>>>(x, ld, n, out, rows);
+  return static_cast<int>(cudaGetLastError());
+}
+
+// ----------------------------------------------------------------------------------- per-image top-k (sorted, descending)
+// torch.topk(score, nq, dim=1) (transformer.py:246): one CTA per image, bitonic sort of (score, index)
+// in shared memory; ties broken towards the lower index.
+__global__ void __launch_bounds__(1024) topk_kernel(const float* __restrict__ score, int S, int np2, int k, int* __restrict__ idx_out) {
+  extern __shared__ uint8_t sm_topk[];
+  float* key = reinterpret_cast<float*>(sm_topk);
+  int* val = reinterpret_cast<int*>(key + np2);
+  const int b = blockIdx.x;
+  for (int i = threadIdx.x; i < np2; i += blockDim.x) {
+    key[i] = i < S ? score[static_cast<long long>(b) * S + i] : -CUDART_INF_F;
+    val[i] = i;
+  }
+  __syncthreads();
+  for (int size = 2; size <= np2; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      for (int i = threadIdx.x; i < np2 / 2; i += blockDim.x) {
+        const int lo = 2 * i - (i & (stride - 1));
+        const int hi = lo + stride;
+        const bool desc = ((lo & size) == 0);          // first half of each `size` block sorted descending
+        const float ka = key[lo], kb = key[hi];
+        const int va = val[lo], vb = val[hi];
+        const bool a_first = (ka > kb) || (ka == kb && va < vb);   // "a ranks before b"
+        if (a_first != desc) {
+          key[lo] = kb; key[hi] = ka;
+          val[lo] = vb; val[hi] = va;
+        }
+      }
+      __syncthreads();
+    }
+  }
+  for (int i = threadIdx.x; i < k; i += blockDim.x) idx_out[static_cast<long long>(b) * k + i] = val[i];
+}
+int topk_launch(const float* score, int B, int S, int k, int* idx_out, cudaStream_t st) {
+  int np2 = 1;
+  while (np2 < S) np2 <<= 1;
+  if (np2 > 16384 || k > S) return -2;
+  const size_t smem = static_cast<size_t>(np2) * 8;
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * 8);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    attr = true;
+  }
+  topk_kernel<<<B, 1024, smem, st>>>(score, S, np2, k, idx_out);
+  return static_cast<int>(cudaGetLastError());
+}
+
+// ----------------------------------------------------------------------------------- gather of the selected rows
+// sel[b,j,:] = feat[b, idx[b,j], :] (16-bit), enc_logits[b,j,:] = logits[b, idx[b,j], :] (fp32).
+template <typename T>
+__global__ void __launch_bounds__(128) gather_topk_kernel(const T* __restrict__ feat, int ldf, const float* __restrict__ logits, int ldl,
+                                                          int ncls, const int* __restrict__ idx, int S, int k, int d,
+                                                          T* __restrict__ sel, float* __restrict__ enc_logits) {
+  const long long bj = blockIdx.x;
+  const long long b = bj / k;
+  const long long src = b * S + idx[bj];
+  for (int c = threadIdx.x; c < d / 8; c += blockDim.x)
+    *reinterpret_cast<U4*>(sel + bj * d + c * 8) = *reinterpret_cast<const U4*>(feat + src * ldf + c * 8);
+  if (enc_logits != nullptr)
+    for (int c = threadIdx.x; c < ncls; c += blockDim.x) enc_logits[bj * ncls + c] = logits[src * ldl + c];
+}
+int gather_topk_launch(int dtype, const void* feat, int ldf, const float* logits, int ldl, int ncls, const int* idx, int B, int S,
+                       int k, int d, void* sel, float* enc_logits, cudaStream_t st) {
+  const unsigned grid = static_cast<unsigned>(B) * k;
+  if (dtype == DT_BF16) gather_topk_kernel<<<grid, 128, 0, st>>>(static_cast<const __nv_bfloat16*>(feat), ldf, logits, ldl, ncls, idx, S, k, d, static_cast<__nv_bfloat16*>(sel), enc_logits);
+  else gather_topk_kernel<<<grid, 128, 0, st>>>(static_cast<const __half*>(feat), ldf, logits, ldl, ncls, idx, S, k, d, static_cast<__half*>(sel), enc_logits);
+  return static_cast<int>(cudaGetLastError());
+}
+
+// ----------------------------------------------------------------------------------- two-stage boxes + query reference + sine embedding
+// For each selected token (transformer.py:234-240, 266-276, 42-68, 344-357):
+//   box_ts   = reparam(delta_ts, proposal[idx])             -> enc_outputs.pred_boxes
+//   refpoint = reparam(refpoint_embed[j], box_ts)           -> decoder reference (kept fp32)
+//   sine     = [sin/cos embedding of (y, x, w, h)], 4*(d/2) = 2d values, 16-bit
+template <typename T>
+__global__ void __launch_bounds__(256) query_init_kernel(const float* __restrict__ delta_ts, const float* __restrict__ proposals,
+                                                         const int* __restrict__ idx, const float* __restrict__ refpoint_embed,
+                                                         int k, int d, long long rows, float* __restrict__ box_ts,
+                                                         float* __restrict__ refpoint, T* __restrict__ sine) {
+  const long long row = blockIdx.x;
+  if (row >= rows) return;
+  const int j = static_cast<int>(row % k);
+  __shared__ float rp[4];
+  if (threadIdx.x < 4) {
+    const int c = threadIdx.x;
+    const float* pr = proposals + static_cast<long long>(idx[row]) * 4;
+    const float* dl = delta_ts + row * 4;
+    const float bx = c < 2 ? dl[c] * pr[c + 2] + pr[c] : expf(dl[c]) * pr[c];
+    box_ts[row * 4 + c] = bx;
+    // refpoint needs box_ts of both halves: recompute the partner instead of syncing twice
+    const float bxy = c < 2 ? bx : dl[c - 2] * pr[c] + pr[c - 2];
+    const float bwh = c < 2 ? expf(dl[c + 2]) * pr[c + 2] : bx;
+    const float e = refpoint_embed[j * 4 + c];
+    const float r = c < 2 ? e * bwh + bxy : expf(e) * bwh;
+    refpoint[row * 4 + c] = r;
+    rp[c] = r;
+  }
+  __syncthreads();
+  const int dim = d / 2;                        // per-coordinate embedding width
+  const float two_pi = 6.283185307179586f;
+  for (int i = threadIdx.x; i < 2 * d; i += blockDim.x) {
+    const int coord_slot = i / dim;             // output order (y, x, w, h)
+    const int e = i % dim;
+    const float c = rp[coord_slot == 0 ? 1 : (coord_slot == 1 ? 0 : coord_slot)];
+    const float dim_t = powf(10000.f, static_cast<float>(2 * (e / 2)) / static_cast<float>(dim));
+    const float v = c * two_pi / dim_t;
+    sine[row * (2 * d) + i] = Cvt<T>::from_f((e & 1) ? cosf(v) : sinf(v));
+  }
+}
+int query_init_launch(int dtype, const float* delta_ts, const float* proposals, const int* idx, const float* refpoint_embed, int B,
+                      int k, int d, float* box_ts, float* refpoint, void* sine, cudaStream_t st) {
+  const long long rows = static_cast<long long>(B) * k;
+  if (dtype == DT_BF16) query_init_kernel<<<static_cast<unsigned>(rows), 256, 0, st>>>(delta_ts, proposals, idx, refpoint_embed, k, d, rows, box_ts, refpoint, static_cast<__nv_bfloat16*>(sine));
+  else query_init_kernel<<<static_cast<unsigned>(rows), 256, 0, st>>>(delta_ts, proposals, idx, refpoint_embed, k, d, rows, box_ts, refpoint, static_cast<__half*>(sine));
+  return static_cast<int>(cudaGetLastError());
+}
+
+// ----------------------------------------------------------------------------------- final boxes (lwdetr.py:149-155)
+__global__ void __launch_bounds__(256) final_boxes_kernel(const float* __restrict__ delta, const float* __restrict__ refpoint,
+                                                          long long rows_per_layer, long long total, float* __restrict__ boxes) {
+  const long long id = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (id >= total) return;
+  const long long row = id >> 2;
+  const int c = static_cast<int>(id & 3);
+  const float* rf = refpoint + (row % rows_per_layer) * 4;
+  const float dl = delta[id];
+  boxes[id] = c < 2 ? dl * rf[c + 2] + rf[c] : expf(dl) * rf[c];
+}
+int final_boxes_launch(const float* delta, const float* refpoint, long long rows_per_layer, int layers, float* boxes, cudaStream_t st) {
+  const long long total = rows_per_layer * layers * 4;
+  final_boxes_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(delta, refpoint, rows_per_layer, total, boxes);
+  return static_cast<int>(cudaGetLastError());
+}
+
+}  // namespace lwb
