@@ -1,0 +1,339 @@
+"""LW-DETR inference throughput benchmark (BASELINE.json: images/sec at 640x640, per-GPU batch, N B200s).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--config small] [--batch 32] [--dtype fp16]
+    python bench.py --impl reference ...      # the reference algorithm's CPU forward (oracle port) on host cores
+    torchrun --nproc-per-node N bench.py --gpus N ...   # one process per GPU, image-sharded replicas
+
+One "step" = one forward pass of `batch` synthetic 640x640 images per GPU through the C-ABI engine
+(random-init weights of the named architecture, b200/synth.py).  `value` = images/s of the whole job
+with the inputs resident in HBM; `e2e` = the same through the public nn.Module call with PINNED HOST
+inputs (H2D of every batch and D2H of the predictions inside the timed region, double buffered).
+Rank 0 prints ONE JSON line.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "lw-detr_b200"))
+
+import torch  # noqa: E402
+
+DEFAULT_BATCH = {"tiny": 32, "small": 32, "medium": 64, "large": 32, "xlarge": 16}
+FLOPS_PER_IMAGE = {"tiny": 21.40e9, "small": 31.76e9, "medium": 83.93e9, "large": 137.51e9, "xlarge": 342.51e9}
+
+
+def peaks():
+    p = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            m = json.load(f)
+        p.update({k: m[k] for k in ("hbm_gbs", "bf16_tflops", "bf16_tflops_sustained") if k in m})
+        p["source"] = "measured"
+    except Exception:
+        pass
+    return p
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clocks / throttle reasons of one GPU with nvidia-smi while the timed region runs."""
+
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
+        "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self._stop = index, [], threading.Event()
+
+    def run(self):
+        try:
+            p = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            return
+        self.proc = p
+        for line in p.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+            if self._stop.is_set():
+                break
+        try:
+            p.kill()
+        except Exception:
+            pass
+
+    def stop(self):
+        self._stop.set()
+        try:
+            self.proc.kill()
+        except Exception:
+            pass
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+                for n, v in zip(names, r[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                continue
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        hot = [v for v in sm if v >= 0.5 * max(sm)]
+        return {"sm_mhz": statistics.median(hot), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_reference_run(cfg_name, steps, warmup, sample_batch, dtype_name):
+    """The reference algorithm on the host cores: the oracle port (oracle/lwdetr_oracle.py), fp32, all threads."""
+    from b200.config import CONFIGS
+    from b200.synth import synth_images, synth_state_dict
+    from oracle import lwdetr_oracle as orc
+    cfg = CONFIGS[cfg_name]
+    torch.set_num_threads(os.cpu_count())
+    sd = synth_state_dict(cfg, 1)
+    x = synth_images(sample_batch, 0)
+    for _ in range(warmup):
+        orc.forward(sd, cfg, x)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        orc.forward(sd, cfg, x)
+    dt = time.perf_counter() - t0
+    return {"value": steps * sample_batch / dt, "unit": "images/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": "%d forward(s) of %d synthetic 640x640 image(s), %s, fp32 torch CPU oracle port" % (steps, sample_batch, cfg_name),
+            "ms_per_step": 1e3 * dt / steps}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="small")
+    ap.add_argument("--batch", type=int, default=0, help="images per GPU per step")
+    ap.add_argument("--dtype", default=None, choices=[None, "fp16", "bf16"])
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--profile-out", default=None, help="write the per-op timing table (JSON) here")
+    a = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    cfg_name = a.config
+    batch = a.batch or DEFAULT_BATCH[cfg_name]
+    dtype_name = a.dtype or ("bf16" if cfg_name == "medium" else "fp16")
+    warmup = max(a.warmup, 3) if a.impl == "ours" else a.warmup
+    base_cfg = {"workload": "LW-DETR-%s forward, batch %d/GPU, 640x640 synthetic, random-init weights" % (cfg_name, batch),
+                "per_gpu_batch": batch, "global_batch": batch * max(world, 1), "parallelism": "image-sharded replicas x%d" % max(world, 1)}
+
+    if a.impl == "reference":
+        if rank != 0:
+            return
+        sample = 2 if cfg_name in ("tiny", "small") else 1
+        r = cpu_reference_run(cfg_name, max(1, a.steps), a.warmup, sample, dtype_name)
+        print(json.dumps({
+            "impl": "reference", "metric": "images/sec (640x640)", "value": r["value"], "unit": "images/s", "n_gpus": a.gpus,
+            "steps": max(1, a.steps), "warmup": a.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": base_cfg,
+            "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": r["value"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}))
+        return
+
+    # ------------------------------------------------------------------------------------ our arm
+    import torch.distributed as dist
+    from b200 import capi
+    from b200.config import CONFIGS
+    from b200.synth import synth_images, synth_state_dict
+    from models.lwdetr import LWDETR
+    cfg = CONFIGS[cfg_name]
+    dt = {"fp16": torch.float16, "bf16": torch.bfloat16}[dtype_name]
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    # weights: rank 0 materialises them, one NCCL broadcast of the flat arena at init
+    model = LWDETR(cfg, compute_dtype=dt).eval()
+    if rank == 0:
+        model.load_state_dict(synth_state_dict(cfg, 1), strict=True)
+    model.to(dev)
+    if world > 1:
+        flat = torch.cat([p.data.reshape(-1) for p in model.parameters()] + [b.data.float().reshape(-1) for b in model.buffers()])
+        dist.broadcast(flat, src=0)
+        off = 0
+        for t in list(model.parameters()) + list(model.buffers()):
+            n = t.numel()
+            t.data.copy_(flat[off:off + n].reshape(t.shape).to(t.dtype))
+            off += n
+        del flat
+    model.assume_frozen = True
+    eng = model.engine()
+    eng.set_option("cuda_graph", 0 if a.no_graph else 1)
+    # inputs: two distinct device batches (fp32, 4.9 MB/image => larger than the 126 MB L2 at batch >= 26)
+    xs = [synth_images(batch, seed=100 * rank + i).to(dev) for i in range(2)]
+    in_bytes = xs[0].numel() * 4
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            fn(i)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        barrier()
+        return ms.item()
+
+    dev_step = lambda i: eng.forward(xs[i & 1], want_aux=False)
+    for i in range(warmup):
+        dev_step(i)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    ms_total = timed(dev_step, a.steps)
+    if rank == 0:
+        sampler.stop()
+    value = world * batch * a.steps / (ms_total * 1e-3)
+
+    # ---- end to end through the public module call: pinned host -> device (double buffered) -> predictions to host
+    host = [synth_images(batch, seed=7 + i).to(dt).pin_memory() for i in range(2)]
+    dbuf = [torch.empty_like(host[0], device=dev) for _ in range(2)]
+    hl = [torch.empty(batch, cfg.num_queries, cfg.num_classes, dtype=torch.float32).pin_memory() for _ in range(2)]
+    hb = [torch.empty(batch, cfg.num_queries, 4, dtype=torch.float32).pin_memory() for _ in range(2)]
+    copy_stream = torch.cuda.Stream(device=dev)
+    main_stream = torch.cuda.current_stream(dev)
+    ready = [torch.cuda.Event() for _ in range(2)]
+    freed = [torch.cuda.Event() for _ in range(2)]
+    h2d = host[0].numel() * host[0].element_size()
+    d2h = hl[0].numel() * 4 + hb[0].numel() * 4
+
+    def upload(i):
+        s = i & 1
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(freed[s])
+            dbuf[s].copy_(host[s], non_blocking=True)
+            ready[s].record(copy_stream)
+
+    def e2e_run(steps):
+        for s in range(2):
+            freed[s].record(main_stream)
+        upload(0)
+        for i in range(steps):
+            s = i & 1
+            if i + 1 < steps:
+                upload(i + 1)
+            main_stream.wait_event(ready[s])
+            out = model(dbuf[s])
+            freed[s].record(main_stream)
+            hl[s].copy_(out["pred_logits"], non_blocking=True)
+            hb[s].copy_(out["pred_boxes"], non_blocking=True)
+
+    e2e_run(3)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    e2e_run(a.steps)
+    e1.record()
+    torch.cuda.synchronize()
+    ms_e2e = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(ms_e2e, op=dist.ReduceOp.MAX)
+    e2e_value = world * batch * a.steps / (ms_e2e.item() * 1e-3)
+
+    # ---- p50 latency at batch 1 (CUDA graph), per GPU
+    lat = None
+    try:
+        x1 = synth_images(1, seed=3).to(dev)
+        for _ in range(5):
+            eng.forward(x1, want_aux=False)
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(50):
+            t0 = time.perf_counter()
+            eng.forward(x1, want_aux=False)
+            torch.cuda.synchronize()
+            ts.append((time.perf_counter() - t0) * 1e3)
+        lat = statistics.median(ts)
+    except Exception as ex:  # noqa
+        lat = None
+
+    # ---- per-kernel timing (CUDA events on the launch stream) for the roofline of the dominant kernel
+    roof, table = None, None
+    if rank == 0:
+        eng.forward(xs[0], want_aux=False)
+        torch.cuda.synchronize()
+        prof = eng.profile_ops(iters=5)
+        pk = peaks()
+        tot = sum(p[3] for p in prof)
+        groups = {}
+        for lab, fl, by, ms in prof:
+            key = lab.split(".")[-1] if lab.startswith("block") or lab.startswith("dec") or lab.startswith("level") else lab
+            if lab.startswith("block") and "." not in lab:
+                key = "fc2"
+            g = groups.setdefault(key, [0.0, 0.0, 0.0, 0])
+            g[0] += ms; g[1] += fl; g[2] += by; g[3] += 1
+        top = max(groups.items(), key=lambda kv: kv[1][0])
+        name, (gms, gfl, gby, n) = top
+        tens_t = gfl / (pk["bf16_tflops"] * 1e12) if gfl else 0.0
+        hbm_t = gby / (pk["hbm_gbs"] * 1e9)
+        if tens_t >= hbm_t:
+            ach = gfl / (gms * 1e-3) / 1e12
+            roof = {"kernel": name, "launches_per_step": n, "bound": "tensor", "achieved": ach, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
+                    "frac": ach / pk["bf16_tflops"], "traffic": None, "share_of_step": gms / tot, "peak_source": pk["source"] + " (burst)"}
+        else:
+            ach = gby / (gms * 1e-3) / 1e9
+            roof = {"kernel": name, "launches_per_step": n, "bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                    "frac": ach / pk["hbm_gbs"], "traffic": None, "share_of_step": gms / tot, "peak_source": pk["source"]}
+        table = [{"op": k, "launches": v[3], "ms": v[0], "share": v[0] / tot, "gflop": v[1] / 1e9, "mbytes": v[2] / 1e6,
+                  "tflops": (v[1] / (v[0] * 1e-3) / 1e12) if v[0] > 0 else 0, "gbps": (v[2] / (v[0] * 1e-3) / 1e9) if v[0] > 0 else 0}
+                 for k, v in sorted(groups.items(), key=lambda kv: -kv[1][0])]
+        if a.profile_out:
+            with open(a.profile_out, "w") as f:
+                json.dump({"config": base_cfg, "dtype": dtype_name, "sum_ms": tot, "ops": table,
+                           "per_op": [{"op": l, "ms": m, "gflop": fl / 1e9, "mbytes": by / 1e6} for l, fl, by, m in prof]}, f, indent=1)
+
+    cpu = None
+    if rank == 0 and world == 1:
+        try:
+            cpu = cpu_reference_run(cfg_name, 2, 1, 2 if cfg_name in ("tiny", "small") else 1, dtype_name)
+            cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        except Exception as ex:
+            cpu = {"error": repr(ex)}
+
+    if rank == 0:
+        n_kernels = len(eng.ops()) - 0
+        cfgd = dict(base_cfg)
+        cfgd.update({"l2": "two alternating fp32 input batches of %.0f MB each (> 126 MB L2 when batch >= 26); activations exceed L2" % (in_bytes / 1e6),
+                     "cuda_graph": not a.no_graph, "model_gflop_per_image": FLOPS_PER_IMAGE[cfg_name] / 1e9,
+                     "whole_model_tensor_frac_of_sustained": value * FLOPS_PER_IMAGE[cfg_name] / (peaks()["bf16_tflops_sustained"] * 1e12)})
+        print(json.dumps({
+            "metric": "images/sec (640x640)", "value": value, "unit": "images/s", "n_gpus": world, "steps": a.steps, "warmup": warmup,
+            "ms_per_step": ms_total / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": dtype_name,
+            "data": "synthetic", "config": cfgd, "clocks": sampler.summary(),
+            "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "note": "public LWDETR module call; pinned host %s images, double-buffered H2D, predictions copied to pinned host" % dtype_name},
+            "gpu_launches": n_kernels * a.steps, "p50_latency_bs1_ms": lat, "roofline": roof, "cpu_baseline": cpu,
+            "top_ops": table[:8] if table else None}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

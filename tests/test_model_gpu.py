@@ -9,11 +9,16 @@ import torch
 pytestmark = pytest.mark.gpu
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
 
-# Stated tolerances (fp32 oracle vs 16-bit CUDA path).  T1/T2 values follow SURVEY.md 8c (3x the
-# deviation of a torch.autocast reference); see DESIGN.md for the measured values.
+# Stated tolerances (fp32 oracle vs the 16-bit CUDA path), protocol of SURVEY.md 8c: 3x the deviation of a
+# torch.autocast(fp16 / bf16) run of the same forward on the same synthetic weights, two-stage indices forced
+# (calibration measured on tiny/small B=2 in the build container, see DESIGN.md "Parity"):
+#   autocast fp16: memory 9.1e-4, score 4.5e-3, dec 1.2e-3, logits rel-L2 6.1e-4 / max-abs 7.1e-3, boxes 2.8e-4
+#   autocast bf16: memory 7.3e-3, score 3.5e-2, dec 1.0e-2, logits rel-L2 5.0e-3 / max-abs 6.6e-2, boxes 2.4e-3
+# "block" (ViT residual stream) is looser than 3x autocast because this path keeps the residual stream in
+# 16 bits between blocks while autocast keeps it in fp32.
 TOL = {
-    torch.float16: dict(block=2e-3, memory=2.5e-3, score=1.2e-2, logits_rel=1.5e-3, logits_abs=1.5e-2, boxes=2e-4, dec=2e-3),
-    torch.bfloat16: dict(block=1.2e-2, memory=1.5e-2, score=6e-2, logits_rel=8e-3, logits_abs=8e-2, boxes=1.5e-3, dec=1.5e-2),
+    torch.float16: dict(block=2e-3, memory=2.7e-3, score=1.4e-2, logits_rel=1.8e-3, logits_abs=2.1e-2, boxes=8.5e-4, dec=3.6e-3),
+    torch.bfloat16: dict(block=1.5e-2, memory=2.2e-2, score=1.0e-1, logits_rel=1.5e-2, logits_abs=2.0e-1, boxes=7e-3, dec=3e-2),
 }
 CASES = [("tiny", 2), ("small", 2), ("medium", 1), ("large", 1), ("xlarge", 1)]
 
