@@ -164,15 +164,8 @@ def main():
     if rank == 0:
         model.load_state_dict(synth_state_dict(cfg, 1), strict=True)
     model.to(dev)
-    if world > 1:
-        flat = torch.cat([p.data.reshape(-1) for p in model.parameters()] + [b.data.float().reshape(-1) for b in model.buffers()])
-        dist.broadcast(flat, src=0)
-        off = 0
-        for t in list(model.parameters()) + list(model.buffers()):
-            n = t.numel()
-            t.data.copy_(flat[off:off + n].reshape(t.shape).to(t.dtype))
-            off += n
-        del flat
+    from b200.dist import broadcast_module_weights
+    broadcast_module_weights(model, src=0)
     model.assume_frozen = True
     eng = model.engine()
     eng.set_option("cuda_graph", 0 if a.no_graph else 1)
