@@ -68,8 +68,16 @@ void bicubic_resize_chlast(const float* src, int n_in, int C, int n_out, float* 
 // ------------------------------------------------------------------------------- Engine basics
 Engine::Engine(const lwdetr_config& cfg, int dtype) : cfg_(cfg), dtype_(dtype) {}
 
+void Engine::drop_graphs() {
+  for (auto& kv : graphs_) cudaGraphExecDestroy(kv.second);
+  graphs_.clear();
+}
+
 Engine::~Engine() {
-  if (graph_exec_) cudaGraphExecDestroy(graph_exec_);
+  drop_graphs();
+  if (gstream_) cudaStreamDestroy(gstream_);
+  if (ev_in_) cudaEventDestroy(ev_in_);
+  if (ev_out_) cudaEventDestroy(ev_out_);
   if (warena_.p) cudaFree(warena_.p);
   if (sarena_.p) cudaFree(sarena_.p);
 }
@@ -116,7 +124,7 @@ float* Engine::upload32(const std::vector<float>& v) {
 int Engine::set_option(const char* name, int value) {
   if (std::strcmp(name, "cuda_graph") == 0) {
     use_graph_ = value;
-    if (graph_exec_) { cudaGraphExecDestroy(graph_exec_); graph_exec_ = nullptr; }
+    drop_graphs();
     return 0;
   }
   return -1;
@@ -144,7 +152,7 @@ int Engine::load_weights(const std::map<std::string, HostTensor>& w, std::string
   // total parameter bytes bound: every tensor at most once in 16-bit + fp32 vectors + slack
   long long total = 0;
   for (auto& kv : w) total += kv.second.numel;
-  if (graph_exec_) { cudaGraphExecDestroy(graph_exec_); graph_exec_ = nullptr; }
+  drop_graphs();
   if (warena_.p) { cudaFree(warena_.p); warena_.p = nullptr; }
   warena_.bytes = static_cast<size_t>(total) * 4 + (64u << 20);
   if (cudaMalloc(&warena_.p, warena_.bytes) != cudaSuccess) { *err = "cudaMalloc(weight arena) failed"; return -1; }
@@ -628,7 +636,8 @@ int Engine::plan(int B, std::string* err) {
       return -1;
     }
   }
-  if (graph_exec_) { cudaGraphExecDestroy(graph_exec_); graph_exec_ = nullptr; }
+  drop_graphs();
+  eager_runs_ = 0;
   planned_B_ = B;
   return 0;
 }
@@ -656,29 +665,40 @@ int Engine::forward(const void* images, int images_fp32, int B, float* pred_logi
   if (B <= 0) { *err = "lwdetr_forward: batch must be positive"; return -1; }
   if (B != planned_B_ && plan(B, err)) return -1;
   in_images_ = images; in_images_fp32_ = images_fp32; in_topk_override_ = topk_override;
-  const bool graph_ok = use_graph_ && captures_.empty();
+  // The first forward of a plan always runs eagerly (it also performs the one-time cudaFuncSetAttribute calls).
+  const bool graph_ok = use_graph_ && captures_.empty() && eager_runs_ > 0;
   if (graph_ok) {
-    if (graph_exec_ && (graph_images_ != images || graph_topk_ != topk_override || graph_images_fp32_ != images_fp32)) {
-      cudaGraphExecDestroy(graph_exec_); graph_exec_ = nullptr;
+    if (!gstream_) {
+      if (cudaStreamCreateWithFlags(&gstream_, cudaStreamNonBlocking) != cudaSuccess ||
+          cudaEventCreateWithFlags(&ev_in_, cudaEventDisableTiming) != cudaSuccess ||
+          cudaEventCreateWithFlags(&ev_out_, cudaEventDisableTiming) != cudaSuccess) { *err = "graph stream setup failed"; return -1; }
     }
-    if (!graph_exec_) {
+    const GraphKey key{images, images_fp32, topk_override};
+    auto it = graphs_.find(key);
+    if (it == graphs_.end()) {
+      if (graphs_.size() >= 8) drop_graphs();
       cudaGraph_t g = nullptr;
-      if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) != cudaSuccess) { *err = "graph capture begin failed"; return -1; }
+      if (cudaStreamBeginCapture(gstream_, cudaStreamCaptureModeThreadLocal) != cudaSuccess) { *err = std::string("graph capture begin failed: ") + cudaGetErrorString(cudaGetLastError()); return -1; }
       int rc = 0;
-      for (auto& op : ops_) { rc = op.run(st); if (rc) break; }
-      cudaError_t ce = cudaStreamEndCapture(st, &g);
+      for (auto& op : ops_) { rc = op.run(gstream_); if (rc) break; }
+      cudaError_t ce = cudaStreamEndCapture(gstream_, &g);
       if (rc || ce != cudaSuccess) { if (g) cudaGraphDestroy(g); *err = "graph capture failed"; return -1; }
-      if (cudaGraphInstantiate(&graph_exec_, g, 0) != cudaSuccess) { cudaGraphDestroy(g); *err = "graph instantiate failed"; return -1; }
+      cudaGraphExec_t ex = nullptr;
+      if (cudaGraphInstantiate(&ex, g, 0) != cudaSuccess) { cudaGraphDestroy(g); *err = "graph instantiate failed"; return -1; }
       cudaGraphDestroy(g);
-      graph_images_ = images; graph_topk_ = topk_override; graph_images_fp32_ = images_fp32;
+      it = graphs_.emplace(key, ex).first;
     }
-    if (cudaGraphLaunch(graph_exec_, st) != cudaSuccess) { *err = "graph launch failed"; return -1; }
+    // order the graph after the caller's stream and the caller's stream after the graph
+    if (cudaEventRecord(ev_in_, st) != cudaSuccess || cudaStreamWaitEvent(gstream_, ev_in_, 0) != cudaSuccess ||
+        cudaGraphLaunch(it->second, gstream_) != cudaSuccess || cudaEventRecord(ev_out_, gstream_) != cudaSuccess ||
+        cudaStreamWaitEvent(st, ev_out_, 0) != cudaSuccess) { *err = std::string("graph launch failed: ") + cudaGetErrorString(cudaGetLastError()); return -1; }
   } else {
     for (auto& op : ops_) {
       const int rc = op.run(st);
       if (rc) { *err = "op " + op.label + " failed to launch: " + (rc > 0 ? cudaGetErrorString(static_cast<cudaError_t>(rc)) : "bad arguments"); return -1; }
       if (!captures_.empty() && do_capture(op, st)) { *err = "capture after " + op.label + " failed: " + cudaGetErrorString(cudaGetLastError()); return -1; }
     }
+    ++eager_runs_;
   }
   // results -> caller buffers (dense)
   const int nq = cfg_.num_queries, ncls = cfg_.num_classes, NL = cfg_.dec_layers;

@@ -66,10 +66,15 @@ class Engine {
   int planned_B_ = 0;
   bool weights_loaded_ = false;
   int use_graph_ = 0;
-  cudaGraphExec_t graph_exec_ = nullptr;
-  const void* graph_images_ = nullptr;
-  const int32_t* graph_topk_ = nullptr;
-  int graph_images_fp32_ = -1;
+  // CUDA graphs: one executable graph per (images pointer, input dtype, top-k override pointer); captured on
+  // an internal stream (the caller's stream may be the legacy default stream, which cannot be captured)
+  struct GraphKey { const void* images; int fp32; const void* topk; bool operator<(const GraphKey& o) const {
+    return images != o.images ? images < o.images : (fp32 != o.fp32 ? fp32 < o.fp32 : topk < o.topk); } };
+  std::map<GraphKey, cudaGraphExec_t> graphs_;
+  cudaStream_t gstream_ = nullptr;
+  cudaEvent_t ev_in_ = nullptr, ev_out_ = nullptr;
+  int eager_runs_ = 0;
+  void drop_graphs();
   std::vector<Op> ops_;
   std::vector<Capture> captures_;
   // arenas
