@@ -51,3 +51,38 @@ def test_parity_ladder(name, batch, dt):
     if "slot_aligned_enc_boxes_maxabs" in t3:
         assert t3["slot_aligned_enc_boxes_maxabs"] <= 2 * tol["boxes"], t3
         assert t3["slot_aligned_enc_logits_maxabs"] <= 2 * tol["logits_abs"], t3
+
+
+def test_cuda_graph_replay_matches_eager_and_drop_in_module_call():
+    """The CUDA-graph path (per input pointer) and the public nn.Module call give bit-identical results to the
+    eager schedule; the module re-packs when weights change."""
+    from b200.config import CONFIGS
+    from b200.synth import synth_images, synth_state_dict
+    from models.lwdetr import LWDETR
+    cfg = CONFIGS["tiny"]
+    model = LWDETR(cfg, compute_dtype=torch.float16).eval()
+    model.load_state_dict(synth_state_dict(cfg, 1), strict=True)
+    model.cuda()
+    xs = [synth_images(2, s).cuda() for s in (0, 1)]
+    eager = [{k: v.clone() for k, v in model(x).items() if k.startswith("pred")} for x in xs]
+    eng = model.engine()
+    eng.set_option("cuda_graph", 1)
+    for rep in range(3):
+        for x, ref in zip(xs, eager):
+            out = model(x)
+            torch.cuda.synchronize()
+            assert torch.equal(out["pred_logits"], ref["pred_logits"]) and torch.equal(out["pred_boxes"], ref["pred_boxes"])
+    # list-of-images input path (util/benchmark.py:608-610 style)
+    out = model([xs[0][0], xs[0][1]])
+    assert torch.equal(out["pred_logits"], eager[0]["pred_logits"])
+    assert set(out) == {"pred_logits", "pred_boxes", "aux_outputs", "enc_outputs"} and len(out["aux_outputs"]) == 2
+    # weights change -> re-pack -> different output
+    with torch.no_grad():
+        model.class_embed.bias.add_(1.0)
+    out2 = model(xs[0])
+    assert (out2["pred_logits"] - eager[0]["pred_logits"] - 1.0).abs().max().item() < 2e-2
+    # padded batches are rejected, not silently mis-computed
+    from util.misc import nested_tensor_from_tensor_list
+    nt = nested_tensor_from_tensor_list([xs[0][0], xs[0][1][:, :600, :]])
+    with pytest.raises(NotImplementedError):
+        model(nt)
