@@ -98,9 +98,21 @@ def cpu_reference_run(cfg_name, steps, warmup, sample_batch, dtype_name):
     from b200.synth import synth_images, synth_state_dict
     from oracle import lwdetr_oracle as orc
     cfg = CONFIGS[cfg_name]
-    torch.set_num_threads(os.cpu_count())
     sd = synth_state_dict(cfg, 1)
     x = synth_images(sample_batch, 0)
+    # "all the host threads it can use": torch's intra-op pool does not scale to every core of a many-core host
+    # on ops this small, so pick the thread count that maximises throughput (one probe forward per candidate).
+    ncpu = os.cpu_count() or 1
+    best_t, best = ncpu, None
+    for t in sorted({c for c in (8, 16, 32, 64, ncpu) if c <= ncpu}):
+        torch.set_num_threads(t)
+        orc.forward(sd, cfg, x)
+        t0 = time.perf_counter()
+        orc.forward(sd, cfg, x)
+        el = time.perf_counter() - t0
+        if best is None or el < best:
+            best, best_t = el, t
+    torch.set_num_threads(best_t)
     for _ in range(warmup):
         orc.forward(sd, cfg, x)
     t0 = time.perf_counter()
@@ -108,7 +120,7 @@ def cpu_reference_run(cfg_name, steps, warmup, sample_batch, dtype_name):
         orc.forward(sd, cfg, x)
     dt = time.perf_counter() - t0
     return {"value": steps * sample_batch / dt, "unit": "images/s", "cores": torch.get_num_threads(), "kind": "port",
-            "sample": "%d forward(s) of %d synthetic 640x640 image(s), %s, fp32 torch CPU oracle port" % (steps, sample_batch, cfg_name),
+            "sample": "%d forward(s) of %d synthetic 640x640 image(s), %s, fp32 torch CPU oracle port, best of thread counts up to %d" % (steps, sample_batch, cfg_name, ncpu),
             "ms_per_step": 1e3 * dt / steps}
 
 

@@ -17,7 +17,7 @@ namespace lwb {
 template <typename T> struct Mma;
 template <> struct Mma<__half> {
   static __device__ __forceinline__ void run(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-    asm volatile(
+    asm(
         "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
         : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
         : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
@@ -25,7 +25,7 @@ template <> struct Mma<__half> {
 };
 template <> struct Mma<__nv_bfloat16> {
   static __device__ __forceinline__ void run(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-    asm volatile(
+    asm(
         "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
         : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
         : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
@@ -101,7 +101,9 @@ __global__ void __launch_bounds__(WARPS * 32) attn_kernel(const AttnArgs p) {
   float o[DH / 8][4];
 #pragma unroll
   for (int i = 0; i < DH / 8; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
-  float m_run[2] = {-INFINITY, -INFINITY}, l_run[2] = {0.f, 0.f};
+  float m_run[2] = {-INFINITY, -INFINITY};
+  float lsum[4] = {0.f, 0.f, 0.f, 0.f};                      // [row g | row g | row g+8 | row g+8] sums of P
+  const uint32_t ones2 = Cvt<T>::pack(1.f, 1.f);
   const int g = lane >> 2, t4 = lane & 3;
 
   for (int ch = 0; ch < nchunks; ++ch) {
@@ -143,43 +145,46 @@ __global__ void __launch_bounds__(WARPS * 32) attn_kernel(const AttnArgs p) {
         Mma<T>::run(s[nt + 1], qf[kk], kf[2], kf[3]);
       }
     }
-    // ---- scale, mask the tail keys, online softmax
+    // ---- online softmax.  Instruction diet (the kernel is MUFU/issue bound at dh = 16): the max runs on the
+    // raw scores, scale and max-subtraction are one FFMA feeding ex2, tail masking only touches the last
+    // chunk, and the row sums come from one extra MMA against a ones fragment (below) instead of FADDs.
     const int kbase = ch * KC;
+    if (kbase + KC > p.seqlen) {
+#pragma unroll
+      for (int nt = 0; nt < KC / 8; ++nt)
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (kbase + nt * 8 + t4 * 2 + (j & 1) >= p.seqlen) s[nt][j] = -INFINITY;
+    }
     float mx[2] = {-INFINITY, -INFINITY};
 #pragma unroll
     for (int nt = 0; nt < KC / 8; ++nt) {
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int key = kbase + nt * 8 + t4 * 2 + (j & 1);
-        const float v = key < p.seqlen ? s[nt][j] * p.scale_log2 : -INFINITY;
-        s[nt][j] = v;
-        mx[j >> 1] = fmaxf(mx[j >> 1], v);
-      }
+      mx[0] = fmaxf(mx[0], fmaxf(s[nt][0], s[nt][1]));
+      mx[1] = fmaxf(mx[1], fmaxf(s[nt][2], s[nt][3]));
     }
-    float alpha[2], rs[2] = {0.f, 0.f};
+    float alpha[2], msc[2];
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
       mx[h] = fmaxf(mx[h], __shfl_xor_sync(0xffffffffu, mx[h], 1));
       mx[h] = fmaxf(mx[h], __shfl_xor_sync(0xffffffffu, mx[h], 2));
-      const float m_new = fmaxf(m_run[h], mx[h]);
-      alpha[h] = fast_exp2(m_run[h] - m_new);
+      const float m_new = fmaxf(m_run[h], mx[h]);            // running max of the RAW scores
+      alpha[h] = fast_exp2((m_run[h] - m_new) * p.scale_log2);
       m_run[h] = m_new;
+      msc[h] = m_new * p.scale_log2;
     }
     uint32_t pf[KC / 16][4];
 #pragma unroll
     for (int nt = 0; nt < KC / 8; ++nt) {
-      const float p0 = fast_exp2(s[nt][0] - m_run[0]);
-      const float p1 = fast_exp2(s[nt][1] - m_run[0]);
-      const float p2 = fast_exp2(s[nt][2] - m_run[1]);
-      const float p3 = fast_exp2(s[nt][3] - m_run[1]);
-      rs[0] += p0 + p1;
-      rs[1] += p2 + p3;
+      const float p0 = fast_exp2(fmaf(s[nt][0], p.scale_log2, -msc[0]));
+      const float p1 = fast_exp2(fmaf(s[nt][1], p.scale_log2, -msc[0]));
+      const float p2 = fast_exp2(fmaf(s[nt][2], p.scale_log2, -msc[1]));
+      const float p3 = fast_exp2(fmaf(s[nt][3], p.scale_log2, -msc[1]));
       // C fragments of n-tiles (2j, 2j+1) form the A fragment of key-step j
       pf[nt >> 1][(nt & 1) * 2 + 0] = Cvt<T>::pack(p0, p1);
       pf[nt >> 1][(nt & 1) * 2 + 1] = Cvt<T>::pack(p2, p3);
     }
 #pragma unroll
-    for (int h = 0; h < 2; ++h) l_run[h] = l_run[h] * alpha[h] + rs[h];
+    for (int j = 0; j < 4; ++j) lsum[j] *= alpha[j >> 1];
 #pragma unroll
     for (int dt = 0; dt < DH / 8; ++dt) {
       o[dt][0] *= alpha[0];
@@ -190,6 +195,7 @@ __global__ void __launch_bounds__(WARPS * 32) attn_kernel(const AttnArgs p) {
     // ---- O += P V
 #pragma unroll
     for (int kt = 0; kt < KC / 16; ++kt) {
+      Mma<T>::run(lsum, pf[kt], ones2, ones2);               // row sums of the rounded P, fp32 accumulate
 #pragma unroll
       for (int dt = 0; dt < DH / 8; dt += 2) {
         // trans x4 = (keys 0-7, dh dt), (keys 8-15, dh dt), (keys 0-7, dh dt+1), (keys 8-15, dh dt+1)
@@ -205,12 +211,7 @@ __global__ void __launch_bounds__(WARPS * 32) attn_kernel(const AttnArgs p) {
   }
 
   // ---- finalise: divide by the row sums, stage through this warp's Q rows, 16-byte coalesced stores
-#pragma unroll
-  for (int h = 0; h < 2; ++h) {
-    l_run[h] += __shfl_xor_sync(0xffffffffu, l_run[h], 1);
-    l_run[h] += __shfl_xor_sync(0xffffffffu, l_run[h], 2);
-    l_run[h] = 1.f / l_run[h];
-  }
+  const float l_run[2] = {1.f / lsum[0], 1.f / lsum[2]};
   T* sO = sQ + warp * 16 * LDS;
 #pragma unroll
   for (int dt = 0; dt < DH / 8; ++dt) {

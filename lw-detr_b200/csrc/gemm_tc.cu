@@ -41,6 +41,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* empty_bar = full_bar + stages;
   uint64_t* acc_bar = empty_bar + stages;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_bar + 1);
+  float* s_bias = reinterpret_cast<float*>(full_bar + 16);   // 128 B of barriers / slot, then bias | gamma
+  float* s_gamma = s_bias + BN;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -159,46 +161,75 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (p.remap_rows) out_row = (static_cast<long long>(b) * p.IH + y) * p.IW + x;
     const long long res_row = p.resid_mod > 0 ? (m % p.resid_mod) : m;
 
+    // Stage this tile's bias / layer-scale columns in shared memory once (4 epilogue warps, named barrier 1):
+    // the per-chunk loop then has no dependent global loads except the (prefetched) residual.
+    for (int i = r; i < BN; i += 128) {
+      const bool in = (n0 + i) < p.N;
+      s_bias[i] = (p.bias != nullptr && in) ? __ldg(p.bias + n0 + i) : 0.f;
+      s_gamma[i] = (p.gamma != nullptr && in) ? __ldg(p.gamma + n0 + i) : 1.f;
+    }
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+
     mbar_wait(acc_bar, 0);
     tc_fence_after();
     const uint32_t taddr_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
+    const T* resid_row = p.resid != nullptr ? reinterpret_cast<const T*>(p.resid) + res_row * p.ld_resid : nullptr;
+    const bool has_gamma = p.gamma != nullptr;
+    const int act = p.act;
 
 #pragma unroll 1
     for (int c = 0; c < BN / 16; ++c) {
+      const int n = n0 + c * 16;
+      const int nrem = p.N - n;                     // may be <= 0 for the padded tail of the last n-tile
+      const bool full = valid && nrem >= 16;
+      // residual prefetch (independent of the accumulator): issue before waiting on TMEM
+      U8 rr;
+      bool rvec = false;
+      if (full && resid_row != nullptr && (reinterpret_cast<uintptr_t>(resid_row + n) & 31) == 0) {
+        rr = ldg256(resid_row + n);
+        rvec = true;
+      }
       float v[16];
-      __syncwarp();                               // tcgen05.ld is .sync.aligned: reconverge first
+      __syncwarp();                                 // tcgen05.ld is .sync.aligned: reconverge first
       tmem_ld_x16(taddr_row + c * 16, v);
       tmem_ld_wait();
-      const int n = n0 + c * 16;
-      if (!valid || n >= p.N) continue;
-      const int nrem = p.N - n;   // >= 1
-      // bias, activation
+      if (!valid || nrem <= 0) continue;
+      {
+        const float4* sb = reinterpret_cast<const float4*>(s_bias + c * 16);
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        float t = v[j];
-        if (p.bias != nullptr && j < nrem) t += __ldg(p.bias + n + j);
-        v[j] = apply_act(t, p.act);
-      }
-      if (p.gamma != nullptr) {
-#pragma unroll
-        for (int j = 0; j < 16; ++j)
-          if (j < nrem) v[j] *= __ldg(p.gamma + n + j);
-      }
-      if (p.resid != nullptr) {
-        const T* rp = reinterpret_cast<const T*>(p.resid) + res_row * p.ld_resid + n;
-        if (nrem >= 16 && (reinterpret_cast<uintptr_t>(rp) & 31) == 0) {
-          const U8 rr = ldg256(rp);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float2 f = Cvt<T>::unpack(rr.v[j]);
-            v[2 * j] += f.x;
-            v[2 * j + 1] += f.y;
-          }
-        } else {
-#pragma unroll
-          for (int j = 0; j < 16; ++j)
-            if (j < nrem) v[j] += Cvt<T>::to_f(rp[j]);
+        for (int j = 0; j < 4; ++j) {
+          const float4 b4 = sb[j];
+          v[4 * j] += b4.x; v[4 * j + 1] += b4.y; v[4 * j + 2] += b4.z; v[4 * j + 3] += b4.w;
         }
+      }
+      if (act == ACT_GELU) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = 0.5f * v[j] * (1.f + erff(v[j] * 0.70710678118654752f));
+      } else if (act == ACT_RELU) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
+      } else if (act == ACT_SILU) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = v[j] / (1.f + __expf(-v[j]));
+      }
+      if (has_gamma) {
+        const float4* sg = reinterpret_cast<const float4*>(s_gamma + c * 16);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float4 g4 = sg[j];
+          v[4 * j] *= g4.x; v[4 * j + 1] *= g4.y; v[4 * j + 2] *= g4.z; v[4 * j + 3] *= g4.w;
+        }
+      }
+      if (rvec) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float2 f = Cvt<T>::unpack(rr.v[j]);
+          v[2 * j] += f.x;
+          v[2 * j + 1] += f.y;
+        }
+      } else if (resid_row != nullptr) {
+        for (int j = 0; j < 16; ++j)
+          if (j < nrem) v[j] += Cvt<T>::to_f(resid_row[n + j]);
       }
       // destination
       long long orow = out_row;
@@ -210,24 +241,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
       if (p.out_fp32) {
         float* op = reinterpret_cast<float*>(p.out) + orow * p.ld_out + ocol;
-        if (nrem >= 16 && (reinterpret_cast<uintptr_t>(op) & 15) == 0) {
+        if (full && (reinterpret_cast<uintptr_t>(op) & 15) == 0) {
 #pragma unroll
           for (int j = 0; j < 4; ++j)
             reinterpret_cast<float4*>(op)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
         } else {
-#pragma unroll
           for (int j = 0; j < 16; ++j)
             if (j < nrem) op[j] = v[j];
         }
       } else {
         T* op = reinterpret_cast<T*>(p.out) + orow * p.ld_out + ocol;
-        if (nrem >= 16 && (reinterpret_cast<uintptr_t>(op) & 31) == 0) {
+        if (full && (reinterpret_cast<uintptr_t>(op) & 31) == 0) {
           U8 o;
 #pragma unroll
           for (int j = 0; j < 8; ++j) o.v[j] = Cvt<T>::pack(v[2 * j], v[2 * j + 1]);
           stg256(op, o);
         } else {
-#pragma unroll
           for (int j = 0; j < 16; ++j)
             if (j < nrem) op[j] = Cvt<T>::from_f(v[j]);
         }
@@ -387,7 +416,7 @@ int gemm_build(const GemmDesc& d, GemmOp* op, std::string* err) {
   stages = std::min(stages, std::max(1, a.kblocks));
   stages = std::min(stages, 6);
   a.stages = stages;
-  op->smem = 1024 + static_cast<size_t>(stages) * stage_bytes + 256;
+  op->smem = 1024 + static_cast<size_t>(stages) * stage_bytes + 128 + 2 * 4 * static_cast<size_t>(bn);
   op->grid = static_cast<unsigned>(m_tiles) * a.n_tiles;
   op->flops = 2.0 * d.M * static_cast<double>(d.N) * d.K;
   return 0;
