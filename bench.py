@@ -306,6 +306,13 @@ def main():
             ach = gby / (gms * 1e-3) / 1e9
             roof = {"kernel": name, "launches_per_step": n, "bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s",
                     "frac": ach / pk["hbm_gbs"], "traffic": None, "share_of_step": gms / tot, "peak_source": pk["source"]}
+        if name.endswith("attn"):
+            # attention at head dim 16/32 is bound by exp (MUFU, 16 ex2/clk/SM), not by the tensor pipe: report that too
+            dh = (cfg.vit_dim // cfg.vit_heads) if name in ("glb_attn", "win_attn") else (cfg.hidden_dim // cfg.sa_nheads)
+            gexp = gfl / (4.0 * dh) / (gms * 1e-3) / 1e9
+            mufu_peak = 16 * 148 * 1.965                      # Gexp/s at the maximum SM clock
+            roof["exp_bound"] = {"achieved_gexp_s": gexp, "peak_gexp_s": mufu_peak, "frac": gexp / mufu_peak,
+                                 "note": "softmax exp count / MUFU.EX2 throughput (16/clk/SM x 148 SMs x 1.965 GHz)"}
         table = [{"op": k, "launches": v[3], "ms": v[0], "share": v[0] / tot, "gflop": v[1] / 1e9, "mbytes": v[2] / 1e6,
                   "tflops": (v[1] / (v[0] * 1e-3) / 1e12) if v[0] > 0 else 0, "gbps": (v[2] / (v[0] * 1e-3) / 1e9) if v[0] > 0 else 0}
                  for k, v in sorted(groups.items(), key=lambda kv: -kv[1][0])]

@@ -56,7 +56,8 @@ __device__ __forceinline__ float fast_exp2(float x) {
   return y;
 }
 
-static constexpr int KC = 64;   // keys per shared-memory chunk
+static constexpr int KC = 64;      // keys per shared-memory chunk
+static constexpr int NSTAGE = 3;   // K/V ring: chunk ch+2 is prefetched while ch is consumed -> one barrier per chunk
 
 template <typename T, int DH, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32) attn_kernel(const AttnArgs p) {
@@ -65,8 +66,8 @@ __global__ void __launch_bounds__(WARPS * 32) attn_kernel(const AttnArgs p) {
   constexpr int CPR = DH / 8;            // 16-byte chunks per row
   extern __shared__ __align__(16) uint8_t smem_attn[];
   T* sQ = reinterpret_cast<T*>(smem_attn);
-  T* sK = sQ + QROWS * LDS;              // [2][KC][LDS]
-  T* sV = sK + 2 * KC * LDS;             // [2][KC][LDS]
+  T* sK = sQ + QROWS * LDS;              // [NSTAGE][KC][LDS]
+  T* sV = sK + NSTAGE * KC * LDS;        // [NSTAGE][KC][LDS]
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int qtile = blockIdx.x, head = blockIdx.y, seq = blockIdx.z;
@@ -96,6 +97,8 @@ __global__ void __launch_bounds__(WARPS * 32) attn_kernel(const AttnArgs p) {
   const int nchunks = (p.seqlen + KC - 1) / KC;
   load_kv(0, 0);
   cp_async_commit();
+  if (nchunks > 1) load_kv(1, 1);
+  cp_async_commit();                     // (possibly empty) group keeps the wait_group arithmetic uniform
 
   uint32_t qf[DH / 16][4];
   float o[DH / 8][4];
@@ -107,15 +110,11 @@ __global__ void __launch_bounds__(WARPS * 32) attn_kernel(const AttnArgs p) {
   const int g = lane >> 2, t4 = lane & 3;
 
   for (int ch = 0; ch < nchunks; ++ch) {
-    const int buf = ch & 1;
-    if (ch + 1 < nchunks) {
-      load_kv(ch + 1, buf ^ 1);
-      cp_async_commit();
-      cp_async_wait<1>();
-    } else {
-      cp_async_wait<0>();
-    }
-    __syncthreads();
+    const int buf = ch % NSTAGE;
+    cp_async_wait<1>();                  // chunk ch has landed (only the newest group may still be in flight)
+    __syncthreads();                     // ... for every thread; also: everyone finished chunk ch-1
+    if (ch + 2 < nchunks) load_kv(ch + 2, (ch + 2) % NSTAGE);   // refills the buffer consumed at ch-1
+    cp_async_commit();
     if (ch == 0) {
       // Q fragments (A operand): ldmatrix x4 = (rows 0-7,k 0-7), (rows 8-15,k 0-7), (rows 0-7,k 8-15), (rows 8-15,k 8-15)
 #pragma unroll
@@ -207,7 +206,6 @@ __global__ void __launch_bounds__(WARPS * 32) attn_kernel(const AttnArgs p) {
         Mma<T>::run(o[dt + 1], pf[kt], vf[2], vf[3]);
       }
     }
-    __syncthreads();   // everyone is done with this buffer before it is refilled
   }
 
   // ---- finalise: divide by the row sums, stage through this warp's Q rows, 16-byte coalesced stores
@@ -232,7 +230,7 @@ __global__ void __launch_bounds__(WARPS * 32) attn_kernel(const AttnArgs p) {
 template <typename T, int DH, int WARPS>
 static int launch(const AttnArgs& a, cudaStream_t st) {
   constexpr int LDS = DH + 8;
-  const size_t smem = static_cast<size_t>(WARPS * 16 + 4 * KC) * LDS * sizeof(T);
+  const size_t smem = static_cast<size_t>(WARPS * 16 + 2 * NSTAGE * KC) * LDS * sizeof(T);
   static bool attr = false;
   if (!attr) {
     cudaError_t e = cudaFuncSetAttribute(attn_kernel<T, DH, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);

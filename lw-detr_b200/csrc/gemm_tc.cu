@@ -1,7 +1,7 @@
 // tcgen05 / TMA GEMM family (see gemm_tc.h).  One CTA computes a 128 x BN output tile:
 //   warp 0 : TMA producer (one elected lane) - fills a ring of {A 128x64, W BNx64} stages
 //   warp 1 : TMEM allocator + tcgen05.mma issuer (one elected lane), accumulator in TMEM
-//   warps 2-5 : epilogue, one TMEM lane quarter each: tcgen05.ld -> bias/act/layer-scale/residual ->
+//   warps 2-9 : epilogue, two warps per TMEM lane quarter: tcgen05.ld -> bias/act/layer-scale/residual ->
 //               16-bit (or fp32) rows to global, with optional row re-ordering / pixel shuffle.
 // Replaces, on the LW-DETR path, every F.linear / nn.Conv2d / nn.ConvTranspose2d call listed in
 // SURVEY.md appendix B (reference: models/backbone/vit.py:120-140,206-220, projector.py:85-132,
@@ -18,13 +18,23 @@ namespace lwb {
 static constexpr int BM = 128;
 static constexpr int BK = 64;
 static constexpr int A_STAGE_BYTES = BM * BK * 2;
-static constexpr int GEMM_THREADS = 192;
+static constexpr int EPI_WARPS = 8;                       // two warps per TMEM lane quarter, half of the columns each
+static constexpr int GEMM_THREADS = 64 + 32 * EPI_WARPS;
 
-__device__ __forceinline__ float apply_act(float v, int act) {
-  if (act == ACT_RELU) return fmaxf(v, 0.f);
-  if (act == ACT_GELU) return 0.5f * v * (1.f + erff(v * 0.70710678118654752f));
-  if (act == ACT_SILU) return v / (1.f + __expf(-v));
-  return v;
+// Exact (erf) GELU, nn.GELU() default used by timm's Mlp (vit.py:184).  gelu(x) = x*Phi(x) with
+// Phi(-|x|) = 0.5*erfc(|x|/sqrt2) from Abramowitz-Stegun 7.1.26 (|erf error| <= 1.5e-7):
+//   gelu(x) = max(x, 0) - |x| * [0.5 * poly(t) * exp(-x^2/2)],  t = 1 / (1 + p|x|/sqrt2)
+// 14 instructions incl. 2 MUFU instead of ~30 for erff(); max abs deviation from the erff form 2.2e-7.
+__device__ __forceinline__ float gelu_erf(float x) {
+  const float ax = fabsf(x);
+  float t, e;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.2316418882f, ax, 1.0f)));       // 0.3275911 / sqrt(2)
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * x * -0.72134752044448170f));        // exp(-x^2/2)
+  float p = fmaf(0.5307027145f, t, -0.7265760135f);                                          // 0.5 * A&S coefficients
+  p = fmaf(p, t, 0.7107068705f);
+  p = fmaf(p, t, -0.142248368f);
+  p = fmaf(p, t, 0.127414796f);
+  return fmaf(-ax * t, p * e, fmaxf(x, 0.f));
 }
 
 template <typename T, int BN>
@@ -128,7 +138,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else {
     // -------------------------------------------------------------------- epilogue
-    const int quarter = warp & 3;               // TMEM lanes [32*quarter, 32*quarter+32)
+    const int quarter = warp & 3;               // TMEM lanes [32*quarter, 32*quarter+32) (hardware: warp_id % 4)
+    const int chalf = (warp - 2) >> 2;          // which half of the tile's 16-column chunks this warp owns
     const int r = quarter * 32 + lane;          // row inside the tile
     int m, b = 0, y = 0, x = 0;
     bool valid;
@@ -163,12 +174,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
     // Stage this tile's bias / layer-scale columns in shared memory once (4 epilogue warps, named barrier 1):
     // the per-chunk loop then has no dependent global loads except the (prefetched) residual.
-    for (int i = r; i < BN; i += 128) {
+    for (int i = threadIdx.x - 64; i < BN; i += 32 * EPI_WARPS) {
       const bool in = (n0 + i) < p.N;
       s_bias[i] = (p.bias != nullptr && in) ? __ldg(p.bias + n0 + i) : 0.f;
       s_gamma[i] = (p.gamma != nullptr && in) ? __ldg(p.gamma + n0 + i) : 1.f;
     }
-    asm volatile("bar.sync 1, 128;" ::: "memory");
+    asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_WARPS) : "memory");
 
     mbar_wait(acc_bar, 0);
     tc_fence_after();
@@ -177,8 +188,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const bool has_gamma = p.gamma != nullptr;
     const int act = p.act;
 
+    constexpr int CH_PER_WARP = BN / 16 / (EPI_WARPS / 4);
 #pragma unroll 1
-    for (int c = 0; c < BN / 16; ++c) {
+    for (int c = chalf * CH_PER_WARP; c < (chalf + 1) * CH_PER_WARP; ++c) {
       const int n = n0 + c * 16;
       const int nrem = p.N - n;                     // may be <= 0 for the padded tail of the last n-tile
       const bool full = valid && nrem >= 16;
@@ -204,7 +216,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
       if (act == ACT_GELU) {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] = 0.5f * v[j] * (1.f + erff(v[j] * 0.70710678118654752f));
+        for (int j = 0; j < 16; ++j) v[j] = gelu_erf(v[j]);
       } else if (act == ACT_RELU) {
 #pragma unroll
         for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
