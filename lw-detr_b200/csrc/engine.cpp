@@ -122,6 +122,12 @@ float* Engine::upload32(const std::vector<float>& v) {
 }
 
 int Engine::set_option(const char* name, int value) {
+  if (std::strcmp(name, "fuse_layernorm") == 0) {
+    fuse_ln_ = value;
+    drop_graphs();
+    planned_B_ = 0;
+    return 0;
+  }
   if (std::strcmp(name, "cuda_graph") == 0) {
     use_graph_ = value;
     drop_graphs();
@@ -154,7 +160,7 @@ int Engine::load_weights(const std::map<std::string, HostTensor>& w, std::string
   for (auto& kv : w) total += kv.second.numel;
   drop_graphs();
   if (warena_.p) { cudaFree(warena_.p); warena_.p = nullptr; }
-  warena_.bytes = static_cast<size_t>(total) * 4 + (64u << 20);
+  warena_.bytes = static_cast<size_t>(total) * 4 + (96u << 20);
   if (cudaMalloc(&warena_.p, warena_.bytes) != cudaSuccess) { *err = "cudaMalloc(weight arena) failed"; return -1; }
   woff_ = 0;
   W_.clear(); F_.clear();
@@ -162,6 +168,10 @@ int Engine::load_weights(const std::map<std::string, HostTensor>& w, std::string
   auto put16 = [&](const std::string& key, const std::vector<float>& v) { void* p = upload16(v); if (!p) oom = true; W_[key] = p; };
   auto put32 = [&](const std::string& key, const std::vector<float>& v) { float* p = upload32(v); if (!p) oom = true; F_[key] = p; };
 
+  const int dtl = dtype_;
+  auto round16 = [dtl](float f) -> float {
+    return dtl == DT_BF16 ? __bfloat162float(__float2bfloat16_rn(f)) : __half2float(__float2half_rn(f));
+  };
   // fold BatchNorm (eval, eps 1e-5) into a bias-free conv: returns (W', b') with W' laid out [Co][k-order]
   auto fold_convx = [&](const std::string& p, int co, int ci, int k, std::vector<float>* Wp, std::vector<float>* bp) {
     auto cw = vec(p + ".conv.weight", 1LL * co * ci * k * k);
@@ -230,6 +240,35 @@ int Engine::load_weights(const std::map<std::string, HostTensor>& w, std::string
       std::copy(qb.begin(), qb.end(), bias.begin());
       std::copy(vb.begin(), vb.end(), bias.begin() + 2 * C);
       put32(k + "qkv.b", bias);
+    }
+    // LayerNorm-fused variants (consumer GEMMs run on the raw residual stream, see gemm_tc.h):
+    //   W'[n,k] = W[n,k]*ln_w[k] ; colsum[n] = sum_k round16(W'[n,k]) ; bias'[n] = bias[n] + sum_k ln_b[k]*W[n,k]
+    auto fold_ln = [&](const std::string& key, const std::vector<float>& Wm, const std::vector<float>& bias, const std::string& ln, int n_out) {
+      auto lw = vec(ln + ".weight", C), lb = vec(ln + ".bias", C);
+      std::vector<float> Wf(Wm.size()), cs(n_out), bf(n_out);
+      for (int n = 0; n < n_out; ++n) {
+        double acc_b = bias[n], acc_c = 0.0;
+        for (int kk = 0; kk < C; ++kk) {
+          const float wv = Wm[static_cast<size_t>(n) * C + kk];
+          const float wf = wv * lw[kk];
+          Wf[static_cast<size_t>(n) * C + kk] = wf;
+          acc_c += round16(wf);
+          acc_b += static_cast<double>(lb[kk]) * wv;
+        }
+        cs[n] = static_cast<float>(acc_c);
+        bf[n] = static_cast<float>(acc_b);
+      }
+      put16(key + ".w", Wf);
+      put32(key + ".b", bf);
+      put32(key + ".cs", cs);
+    };
+    {
+      auto qb = vec(b + "attn.q_bias", C), vb = vec(b + "attn.v_bias", C);
+      std::vector<float> bias(static_cast<size_t>(3) * C, 0.f);
+      std::copy(qb.begin(), qb.end(), bias.begin());
+      std::copy(vb.begin(), vb.end(), bias.begin() + 2 * C);
+      fold_ln(k + "qkv_ln", vec(b + "attn.qkv.weight", 3LL * C * C), bias, b + "norm1", 3 * C);
+      fold_ln(k + "fc1_ln", vec(b + "mlp.fc1.weight", 4LL * C * C), vec(b + "mlp.fc1.bias", 4LL * C), b + "norm2", 4 * C);
     }
     put_linear(k + "proj", b + "attn.proj", C, C);
     put32(k + "g1", vec(b + "gamma_1", C));
@@ -379,7 +418,9 @@ int Engine::plan(int B, std::string* err) {
       const float* gamma = nullptr; Mat resid{nullptr, 0}; int resid_mod = 0; int act = ACT_NONE; int out_fp32 = 0;
       int rows_in = ROWS_PLAIN, remap = 0, shuffle = 0, IH = 0, IW = 0;
       int conv = 0, cB = 0, cOH = 0, cOW = 0;   // conv: 1 = 3x3 s1, 2 = 3x3 s2
+      float2* stats_out = nullptr; const float2* stats_in = nullptr; int ln_C = 0; float ln_eps = 0.f;
     };
+    int stats_parts = 0;   // partial (sum, sumsq) pairs per row written by the N = C producer GEMMs
     auto add_gemm = [&](const std::string& label, Mat A, long long Mrows, int K, const std::string& wkey, int N, void* out, int ld_out,
                         const GemmOpt& o, long long out_rows = -1) {
       if (pass == 0) return;
@@ -390,9 +431,15 @@ int Engine::plan(int B, std::string* err) {
       g.out = out; g.ld_out = ld_out; g.out_fp32 = o.out_fp32; g.rows_in = o.rows_in; g.remap_rows = o.remap;
       g.shuffle_cout = o.shuffle; g.IH = o.IH; g.IW = o.IW;
       if (o.conv) { g.a_mode = o.conv == 1 ? AMODE_CONV3_S1 : AMODE_CONV3_S2; g.B = o.cB; g.OH = o.cOH; g.OW = o.cOW; }
+      g.stats_out = o.stats_out; g.stats_in = o.stats_in; g.stats_parts_in = stats_parts; g.ln_C = o.ln_C; g.ln_eps = o.ln_eps;
+      if (o.stats_in) g.colsum = w32(wkey + ".cs");
       GemmOp op;
       std::string e;
       if (fail || gemm_build(g, &op, &e)) { if (!fail) *err = label + ": " + e; fail = true; return; }
+      if (o.stats_out) {
+        if (stats_parts == 0) stats_parts = op.args.stats_parts_out;
+        if (stats_parts != op.args.stats_parts_out || stats_parts > 24) { *err = label + ": inconsistent LayerNorm partial count"; fail = true; return; }
+      }
       Op P_;
       P_.label = label;
       P_.run = [op](cudaStream_t st) { return gemm_launch(op, st); };
@@ -453,28 +500,44 @@ int Engine::plan(int B, std::string* err) {
       add_op("patch_gather", [this, a0p, B, img, dt](cudaStream_t st) { return patch_gather_launch(dt, in_images_, in_images_fp32_, a0p, B, img, st); },
              a0.p, BT, 768, 768, 0, 1.0 * B * 3 * img * img * 4 + 2.0 * BT * 768);
     }
+    float2* stats_x = static_cast<float2*>(salloc(static_cast<size_t>(BT) * 24 * sizeof(float2)));   // row stats of x (block input)
+    float2* stats_m = static_cast<float2*>(salloc(static_cast<size_t>(BT) * 24 * sizeof(float2)));   // row stats of x + attn
+    const bool fuse = fuse_ln_ != 0;
     Mat xcur = xa;
     {
       GemmOpt o; o.resid = Mat{pass ? w16("pos") : nullptr, C}; o.resid_mod = T;
+      if (fuse) o.stats_out = stats_x;
       add_gemm("patch_embed", a0, BT, 768, "patch", C, xcur.p, xcur.ld, o);
     }
     int tap_slot = 0;
     for (int i = 0; i < cfg_.vit_depth; ++i) {
       const std::string k = "blk" + std::to_string(i) + ".", lb = "block" + std::to_string(i);
       const bool window = (cfg_.window_block_mask >> i) & 1;
-      add_ln(lb + ".ln1", xcur, lnb, k + "ln1", 1e-6f, BT, C);
-      add_gemm(lb + ".qkv", lnb, BT, C, k + "qkv", 3 * C, qkv.p, qkv.ld, GemmOpt{});
+      if (fuse) {
+        GemmOpt o; o.stats_in = stats_x; o.ln_C = C; o.ln_eps = 1e-6f;
+        add_gemm(lb + ".qkv", xcur, BT, C, k + "qkv_ln", 3 * C, qkv.p, qkv.ld, o);
+      } else {
+        add_ln(lb + ".ln1", xcur, lnb, k + "ln1", 1e-6f, BT, C);
+        add_gemm(lb + ".qkv", lnb, BT, C, k + "qkv", 3 * C, qkv.p, qkv.ld, GemmOpt{});
+      }
       add_attn(lb + (window ? ".win_attn" : ".glb_attn"), col(qkv, 0), col(qkv, C), col(qkv, 2 * C), att,
                window ? 16 * B : B, window ? T / 16 : T, heads, C / heads);
-      { GemmOpt o; o.gamma = pass ? w32(k + "g1") : nullptr; o.resid = xcur; add_gemm(lb + ".proj", att, BT, C, k + "proj", C, xm.p, xm.ld, o); }
-      add_ln(lb + ".ln2", xm, lnb, k + "ln2", 1e-6f, BT, C);
-      { GemmOpt o; o.act = ACT_GELU; add_gemm(lb + ".fc1", lnb, BT, C, k + "fc1", 4 * C, hid.p, hid.ld, o); }
+      { GemmOpt o; o.gamma = pass ? w32(k + "g1") : nullptr; o.resid = xcur; if (fuse) o.stats_out = stats_m;
+        add_gemm(lb + ".proj", att, BT, C, k + "proj", C, xm.p, xm.ld, o); }
+      if (fuse) {
+        GemmOpt o; o.act = ACT_GELU; o.stats_in = stats_m; o.ln_C = C; o.ln_eps = 1e-6f;
+        add_gemm(lb + ".fc1", xm, BT, C, k + "fc1_ln", 4 * C, hid.p, hid.ld, o);
+      } else {
+        add_ln(lb + ".ln2", xm, lnb, k + "ln2", 1e-6f, BT, C);
+        GemmOpt o; o.act = ACT_GELU; add_gemm(lb + ".fc1", lnb, BT, C, k + "fc1", 4 * C, hid.p, hid.ld, o);
+      }
       Mat xnext;
       bool is_tap = false;
       for (int t = 0; t < ntap; ++t) is_tap = is_tap || cfg_.taps[t] == i;
       if (is_tap) xnext = col(tapbuf, (tap_slot++) * C);
       else xnext = (xcur.p == xa.p) ? xb : xa;
-      { GemmOpt o; o.gamma = pass ? w32(k + "g2") : nullptr; o.resid = xm; add_gemm(lb, hid, BT, 4 * C, k + "fc2", C, xnext.p, xnext.ld, o); }
+      { GemmOpt o; o.gamma = pass ? w32(k + "g2") : nullptr; o.resid = xm; if (fuse && i + 1 < cfg_.vit_depth) o.stats_out = stats_x;
+        add_gemm(lb, hid, BT, 4 * C, k + "fc2", C, xnext.p, xnext.ld, o); }
       xcur = xnext;
     }
 

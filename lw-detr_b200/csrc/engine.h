@@ -66,6 +66,7 @@ class Engine {
   int planned_B_ = 0;
   bool weights_loaded_ = false;
   int use_graph_ = 0;
+  int fuse_ln_ = 1;   // ViT LayerNorms folded into the consuming GEMM's epilogue (option "fuse_layernorm")
   // CUDA graphs: one executable graph per (images pointer, input dtype, top-k override pointer); captured on
   // an internal stream (the caller's stream may be the legacy default stream, which cannot be captured)
   struct GraphKey { const void* images; int fp32; const void* topk; bool operator<(const GraphKey& o) const {

@@ -53,6 +53,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_bar + 1);
   float* s_bias = reinterpret_cast<float*>(full_bar + 16);   // 128 B of barriers / slot, then bias | gamma
   float* s_gamma = s_bias + BN;
+  float* s_csum = s_gamma + BN;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -178,7 +179,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const bool in = (n0 + i) < p.N;
       s_bias[i] = (p.bias != nullptr && in) ? __ldg(p.bias + n0 + i) : 0.f;
       s_gamma[i] = (p.gamma != nullptr && in) ? __ldg(p.gamma + n0 + i) : 1.f;
+      s_csum[i] = (p.colsum != nullptr && in) ? __ldg(p.colsum + n0 + i) : 0.f;
     }
+    // fused LayerNorm (consumer): combine the producer's partial sums of this row
+    float ln_mean = 0.f, ln_rstd = 1.f;
+    const bool ln_in = p.stats_in != nullptr;
+    if (ln_in && valid) {
+      float s1 = 0.f, s2 = 0.f;
+      for (int i = 0; i < p.stats_parts_in; ++i) {
+        const float2 q = __ldg(p.stats_in + static_cast<long long>(m) * p.stats_parts_in + i);
+        s1 += q.x;
+        s2 += q.y;
+      }
+      ln_mean = s1 * p.ln_inv_c;
+      ln_rstd = rsqrtf(fmaxf(s2 * p.ln_inv_c - ln_mean * ln_mean, 0.f) + p.ln_eps);
+    }
+    float st_sum = 0.f, st_sq = 0.f;
     asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_WARPS) : "memory");
 
     mbar_wait(acc_bar, 0);
@@ -206,6 +222,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       tmem_ld_x16(taddr_row + c * 16, v);
       tmem_ld_wait();
       if (!valid || nrem <= 0) continue;
+      if (ln_in) {
+        const float4* sc = reinterpret_cast<const float4*>(s_csum + c * 16);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float4 c4 = sc[j];
+          v[4 * j] = ln_rstd * fmaf(-ln_mean, c4.x, v[4 * j]);
+          v[4 * j + 1] = ln_rstd * fmaf(-ln_mean, c4.y, v[4 * j + 1]);
+          v[4 * j + 2] = ln_rstd * fmaf(-ln_mean, c4.z, v[4 * j + 2]);
+          v[4 * j + 3] = ln_rstd * fmaf(-ln_mean, c4.w, v[4 * j + 3]);
+        }
+      }
       {
         const float4* sb = reinterpret_cast<const float4*>(s_bias + c * 16);
 #pragma unroll
@@ -268,12 +295,28 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
           for (int j = 0; j < 8; ++j) o.v[j] = Cvt<T>::pack(v[2 * j], v[2 * j + 1]);
           stg256(op, o);
+          if (p.stats_out != nullptr) {             // statistics of the ROUNDED values the consumer will read
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float2 f = Cvt<T>::unpack(o.v[j]);
+              st_sum += f.x + f.y;
+              st_sq = fmaf(f.x, f.x, fmaf(f.y, f.y, st_sq));
+            }
+          }
         } else {
           for (int j = 0; j < 16; ++j)
-            if (j < nrem) op[j] = Cvt<T>::from_f(v[j]);
+            if (j < nrem) {
+              const T h = Cvt<T>::from_f(v[j]);
+              op[j] = h;
+              const float f = Cvt<T>::to_f(h);
+              st_sum += f;
+              st_sq = fmaf(f, f, st_sq);
+            }
         }
       }
     }
+    if (p.stats_out != nullptr && valid)
+      p.stats_out[static_cast<long long>(m) * p.stats_parts_out + n_tile * (EPI_WARPS / 4) + chalf] = make_float2(st_sum, st_sq);
     tc_fence_before();
   }
 
@@ -358,6 +401,10 @@ int gemm_build(const GemmDesc& d, GemmOp* op, std::string* err) {
   a.bias = d.bias; a.gamma = d.gamma; a.resid = d.resid; a.ld_resid = d.ld_resid; a.resid_mod = d.resid_mod;
   a.act = d.act; a.out = d.out; a.ld_out = d.ld_out; a.out_fp32 = d.out_fp32;
   a.rows_in = d.rows_in; a.remap_rows = d.remap_rows; a.shuffle_cout = d.shuffle_cout; a.IH = d.IH; a.IW = d.IW;
+  a.stats_out = d.stats_out; a.stats_in = d.stats_in; a.stats_parts_in = d.stats_parts_in; a.colsum = d.colsum;
+  a.ln_inv_c = d.ln_C > 0 ? 1.f / d.ln_C : 0.f; a.ln_eps = d.ln_eps;
+  if ((d.stats_out || d.stats_in) && (d.a_mode != AMODE_PLAIN || d.remap_rows || d.shuffle_cout || d.out_fp32)) { *err = "gemm: LN fusion needs a plain 16-bit GEMM"; return -1; }
+  if (d.stats_in && (!d.colsum || d.stats_parts_in <= 0 || d.ln_C <= 0)) { *err = "gemm: LN consumer needs colsum / parts / C"; return -1; }
   op->dtype = d.dtype;
   if ((d.remap_rows || d.shuffle_cout) && (d.IH <= 0 || d.IW <= 0 || d.M % (d.IH * d.IW) != 0)) {
     *err = "gemm: row remap needs IH/IW with M a multiple of IH*IW"; return -1;
@@ -417,6 +464,7 @@ int gemm_build(const GemmDesc& d, GemmOp* op, std::string* err) {
   const int bn = pick_bn(d.N, m_tiles);
   op->bn = bn;
   a.n_tiles = (d.N + bn - 1) / bn;
+  a.stats_parts_out = a.n_tiles * (EPI_WARPS / 4);
   {
     const cuuint64_t dims[2] = {static_cast<cuuint64_t>(d.K), static_cast<cuuint64_t>(d.N)};
     const cuuint64_t strides[1] = {static_cast<cuuint64_t>(d.K) * 2};
@@ -428,7 +476,7 @@ int gemm_build(const GemmDesc& d, GemmOp* op, std::string* err) {
   stages = std::min(stages, std::max(1, a.kblocks));
   stages = std::min(stages, 6);
   a.stages = stages;
-  op->smem = 1024 + static_cast<size_t>(stages) * stage_bytes + 128 + 2 * 4 * static_cast<size_t>(bn);
+  op->smem = 1024 + static_cast<size_t>(stages) * stage_bytes + 128 + 3 * 4 * static_cast<size_t>(bn);
   op->grid = static_cast<unsigned>(m_tiles) * a.n_tiles;
   op->flops = 2.0 * d.M * static_cast<double>(d.N) * d.K;
   return 0;

@@ -35,6 +35,16 @@ struct GemmArgs {
   int remap_rows;           // 1: write rows in spatial (b,y,x) order (needs rows_in grid IH x IW)
   int shuffle_cout;         // >0: ConvTranspose2d(k=2,s=2) pixel shuffle, n = (dy*2+dx)*cout + co
   int IH, IW;               // token grid per image for rows_in / shuffle (40 x 40 for the ViT)
+  // LayerNorm fusion (ViT blocks).  Producer side: the epilogue also emits per-row partial (sum, sum of
+  // squares) of the rounded output, one float2 per (row, n_tile, column half).  Consumer side: the GEMM runs
+  // on the RAW rows and applies  out = rstd*(acc - mean*colsum[n]) + bias[n]  where the LN weight is folded into
+  // W, colsum[n] = sum_k W'[n,k] and bias already contains sum_k ln_b[k]*W[n,k].
+  float2* stats_out;        // [M, stats_parts_out] or null
+  int stats_parts_out;
+  const float2* stats_in;   // [M, stats_parts_in] or null
+  int stats_parts_in;
+  const float* colsum;      // [N] fp32 (consumer)
+  float ln_inv_c, ln_eps;   // 1/C of the normalised dimension, epsilon
 };
 
 // Host description of one GEMM.
@@ -55,6 +65,12 @@ struct GemmDesc {
   int ld_out = 0;
   int out_fp32 = 0;
   int rows_in = ROWS_PLAIN, remap_rows = 0, shuffle_cout = 0, IH = 0, IW = 0;
+  float2* stats_out = nullptr;          // producer: buffer with room for M * 2 * n_tiles float2
+  const float2* stats_in = nullptr;     // consumer
+  int stats_parts_in = 0;
+  const float* colsum = nullptr;
+  int ln_C = 0;
+  float ln_eps = 0.f;
 };
 
 struct GemmOp {
