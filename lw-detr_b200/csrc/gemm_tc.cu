@@ -1,4 +1,4 @@
-// tcgen05 / TMA GEMM family (see gemm_tc.h).  One CTA computes a 128 x BN output tile:
+// tcgen05 / TMA GEMM family (see gemm_tc.h).  Persistent CTAs (one per SM) compute 128 x BN output tiles:
 //   warp 0 : TMA producer (one elected lane) - fills a ring of {A 128x64, W BNx64} stages
 //   warp 1 : TMEM allocator + tcgen05.mma issuer (one elected lane), accumulator in TMEM
 //   warps 2-9 : epilogue, two warps per TMEM lane quarter: tcgen05.ld -> bias/act/layer-scale/residual ->
@@ -20,6 +20,7 @@ static constexpr int BK = 64;
 static constexpr int A_STAGE_BYTES = BM * BK * 2;
 static constexpr int EPI_WARPS = 8;                       // two warps per TMEM lane quarter, half of the columns each
 static constexpr int GEMM_THREADS = 64 + 32 * EPI_WARPS;
+static constexpr int MAX_STAGES = 8;
 
 // Exact (erf) GELU, nn.GELU() default used by timm's Mlp (vit.py:184).  gelu(x) = x*Phi(x) with
 // Phi(-|x|) = 0.5*erfc(|x|/sqrt2) from Abramowitz-Stegun 7.1.26 (|erf error| <= 1.5e-7):
@@ -37,39 +38,49 @@ __device__ __forceinline__ float gelu_erf(float x) {
   return fmaf(-ax * t, p * e, fmaxf(x, 0.f));
 }
 
+struct TileCoord {
+  int m_tile, n_tile, n0, cb, cy0, cx0;
+};
+__device__ __forceinline__ TileCoord decode_tile(const GemmArgs& p, int tile, int BN) {
+  TileCoord t;
+  t.n_tile = tile % p.n_tiles;      // n fastest: neighbouring CTAs share the A rows in L2
+  t.m_tile = tile / p.n_tiles;
+  t.n0 = t.n_tile * BN;
+  t.cb = t.cy0 = t.cx0 = 0;
+  if (p.a_mode != AMODE_PLAIN) {
+    const int per_img = p.tiles_x * p.tiles_y;
+    t.cb = t.m_tile / per_img;
+    const int r = t.m_tile % per_img;
+    t.cy0 = (r / p.tiles_x) * p.TH;
+    t.cx0 = (r % p.tiles_x) * p.TW;
+  }
+  return t;
+}
+
+// Persistent: one CTA per SM walks tiles blockIdx.x, +gridDim.x, ...  The smem ring (TMA -> MMA) runs
+// continuously across tiles and the accumulator is double buffered in TMEM, so the epilogue of tile i
+// overlaps the loads and MMAs of tile i+1.
 template <typename T, int BN>
-__global__ void __launch_bounds__(GEMM_THREADS)
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmArgs p) {
   constexpr int B_STAGE_BYTES = BN * BK * 2;
-  constexpr uint32_t TMEM_COLS = BN <= 64 ? 64 : (BN <= 128 ? 128 : 256);
+  constexpr uint32_t ACC_STRIDE = BN <= 64 ? 64 : (BN <= 128 ? 128 : 256);   // TMEM columns per accumulator buffer
+  constexpr uint32_t TMEM_COLS = 2 * ACC_STRIDE;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int stages = p.stages;
   uint8_t* sA = smem;
   uint8_t* sB = smem + stages * A_STAGE_BYTES;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(sB + stages * B_STAGE_BYTES);
-  uint64_t* empty_bar = full_bar + stages;
-  uint64_t* acc_bar = empty_bar + stages;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_bar + 1);
-  float* s_bias = reinterpret_cast<float*>(full_bar + 16);   // 128 B of barriers / slot, then bias | gamma
-  float* s_gamma = s_bias + BN;
-  float* s_csum = s_gamma + BN;
+  uint64_t* empty_bar = full_bar + MAX_STAGES;
+  uint64_t* acc_full = empty_bar + MAX_STAGES;      // [2]
+  uint64_t* acc_empty = acc_full + 2;               // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  float* s_vec = reinterpret_cast<float*>(full_bar + 32);   // 256 B of barriers, then 2 x {bias | gamma | colsum}[BN]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int n_tile = blockIdx.x % p.n_tiles;
-  const int m_tile = blockIdx.x / p.n_tiles;
-  const int n0 = n_tile * BN;
-
-  // conv tile decode (also used by the epilogue)
-  int cb = 0, cy0 = 0, cx0 = 0;
-  if (p.a_mode != AMODE_PLAIN) {
-    const int per_img = p.tiles_x * p.tiles_y;
-    cb = m_tile / per_img;
-    const int t = m_tile % per_img;
-    cy0 = (t / p.tiles_x) * p.TH;
-    cx0 = (t % p.tiles_x) * p.TW;
-  }
+  const int num_tiles = p.m_tiles * p.n_tiles;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -78,7 +89,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
-    mbar_init(acc_bar, 1);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&acc_full[b], 1);
+      mbar_init(&acc_empty[b], EPI_WARPS);
+    }
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -93,231 +107,256 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 0) {
     if (lane == 0) {
       // ------------------------------------------------------------------ TMA producer
-      for (int kb = 0; kb < p.kblocks; ++kb) {
-        const int s = kb % stages;
-        const uint32_t ph = (kb / stages) & 1;
-        mbar_wait(&empty_bar[s], ph ^ 1);
-        mbar_arrive_expect_tx(&full_bar[s], p.a_stage_tx + B_STAGE_BYTES);
-        uint8_t* a_dst = sA + s * A_STAGE_BYTES;
-        if (p.a_mode == AMODE_PLAIN) {
-          tma_load_2d(a_dst, &tmA, &full_bar[s], kb * BK, m_tile * BM);
-        } else {
-          const int tap = kb / p.cin_blocks;
-          const int c0 = (kb % p.cin_blocks) * BK;
-          const int dy = tap / 3, dx = tap % 3;
-          if (p.a_mode == AMODE_CONV3_S1) {
-            tma_load_4d(a_dst, &tmA, &full_bar[s], c0, cx0 + dx - 1, cy0 + dy - 1, cb);
+      uint32_t ring = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const TileCoord tc = decode_tile(p, tile, BN);
+        for (int kb = 0; kb < p.kblocks; ++kb, ++ring) {
+          const int s = ring % stages;
+          const uint32_t ph = (ring / stages) & 1;
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          mbar_arrive_expect_tx(&full_bar[s], p.a_stage_tx + B_STAGE_BYTES);
+          uint8_t* a_dst = sA + s * A_STAGE_BYTES;
+          if (p.a_mode == AMODE_PLAIN) {
+            tma_load_2d(a_dst, &tmA, &full_bar[s], kb * BK, tc.m_tile * BM);
           } else {
-            // input row iy = 2*oy + dy - 1 = 2*(oy + yoff) + py ; same for columns
-            const int py = (dy == 1) ? 0 : 1, yoff = (dy == 0) ? -1 : 0;
-            const int px = (dx == 1) ? 0 : 1, xoff = (dx == 0) ? -1 : 0;
-            tma_load_5d(a_dst, &tmA, &full_bar[s], px * p.lda + c0, cx0 + xoff, py, cy0 + yoff, cb);
+            const int tap = kb / p.cin_blocks;
+            const int c0 = (kb % p.cin_blocks) * BK;
+            const int dy = tap / 3, dx = tap % 3;
+            if (p.a_mode == AMODE_CONV3_S1) {
+              tma_load_4d(a_dst, &tmA, &full_bar[s], c0, tc.cx0 + dx - 1, tc.cy0 + dy - 1, tc.cb);
+            } else {
+              // input row iy = 2*oy + dy - 1 = 2*(oy + yoff) + py ; same for columns
+              const int py = (dy == 1) ? 0 : 1, yoff = (dy == 0) ? -1 : 0;
+              const int px = (dx == 1) ? 0 : 1, xoff = (dx == 0) ? -1 : 0;
+              tma_load_5d(a_dst, &tmA, &full_bar[s], px * p.lda + c0, tc.cx0 + xoff, py, tc.cy0 + yoff, tc.cb);
+            }
           }
+          tma_load_2d(sB + s * B_STAGE_BYTES, &tmB, &full_bar[s], kb * BK, tc.n0);
         }
-        tma_load_2d(sB + s * B_STAGE_BYTES, &tmB, &full_bar[s], kb * BK, n0);
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
       // ------------------------------------------------------------------ MMA issuer
       constexpr uint32_t idesc = umma_idesc_f16(Cvt<T>::is_bf16, BM, BN);
-      for (int kb = 0; kb < p.kblocks; ++kb) {
-        const int s = kb % stages;
-        const uint32_t ph = (kb / stages) & 1;
-        mbar_wait(&full_bar[s], ph);
+      uint32_t ring = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        const int buf = it & 1;
+        mbar_wait(&acc_empty[buf], ((it >> 1) & 1) ^ 1);     // epilogue has drained this accumulator buffer
         tc_fence_after();
-        const uint64_t adesc = umma_desc_k128(smem_u32(sA + s * A_STAGE_BYTES));
-        const uint64_t bdesc = umma_desc_k128(smem_u32(sB + s * B_STAGE_BYTES));
+        const uint32_t tacc = tmem_base + buf * ACC_STRIDE;
+        for (int kb = 0; kb < p.kblocks; ++kb, ++ring) {
+          const int s = ring % stages;
+          const uint32_t ph = (ring / stages) & 1;
+          mbar_wait(&full_bar[s], ph);
+          tc_fence_after();
+          const uint64_t adesc = umma_desc_k128(smem_u32(sA + s * A_STAGE_BYTES));
+          const uint64_t bdesc = umma_desc_k128(smem_u32(sB + s * B_STAGE_BYTES));
 #pragma unroll
-        for (int k = 0; k < BK / 16; ++k) {
-          // advance 16 elements (32 B) along K inside the 128 B swizzle row: +2 in 16-byte units
-          umma_f16_ss(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          for (int k = 0; k < BK / 16; ++k) {
+            // advance 16 elements (32 B) along K inside the 128 B swizzle row: +2 in 16-byte units
+            umma_f16_ss(tacc, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[s]);
         }
-        umma_commit(&empty_bar[s]);
+        umma_commit(&acc_full[buf]);
       }
-      umma_commit(acc_bar);
     }
   } else {
-    // -------------------------------------------------------------------- epilogue
+    // -------------------------------------------------------------------- epilogue (8 warps)
     const int quarter = warp & 3;               // TMEM lanes [32*quarter, 32*quarter+32) (hardware: warp_id % 4)
     const int chalf = (warp - 2) >> 2;          // which half of the tile's 16-column chunks this warp owns
     const int r = quarter * 32 + lane;          // row inside the tile
-    int m, b = 0, y = 0, x = 0;
-    bool valid;
-    if (p.a_mode == AMODE_PLAIN) {
-      m = m_tile * BM + r;
-      valid = m < p.M;
-      if (p.remap_rows || p.shuffle_cout) {
-        const int per = p.IH * p.IW;
-        b = m / per;
-        const int rem = m - b * per;
-        if (p.rows_in == ROWS_WINDOW_MAJOR) {
-          const int wh = p.IH >> 2, ww = p.IW >> 2, wsz = wh * ww;
-          const int win = rem / wsz, t = rem - win * wsz;
-          y = (win >> 2) * wh + t / ww;
-          x = (win & 3) * ww + t % ww;
-        } else {
-          y = rem / p.IW;
-          x = rem - y * p.IW;
-        }
-      }
-    } else {
-      const int ry = r / p.TW;
-      y = cy0 + ry;
-      x = cx0 + (r - ry * p.TW);
-      b = cb;
-      valid = (r < p.TW * p.TH) && (y < p.OH) && (x < p.OW);
-      m = (b * p.OH + y) * p.OW + x;
-    }
-    long long out_row = m;
-    if (p.remap_rows) out_row = (static_cast<long long>(b) * p.IH + y) * p.IW + x;
-    const long long res_row = p.resid_mod > 0 ? (m % p.resid_mod) : m;
-
-    // Stage this tile's bias / layer-scale columns in shared memory once (4 epilogue warps, named barrier 1):
-    // the per-chunk loop then has no dependent global loads except the (prefetched) residual.
-    for (int i = threadIdx.x - 64; i < BN; i += 32 * EPI_WARPS) {
-      const bool in = (n0 + i) < p.N;
-      s_bias[i] = (p.bias != nullptr && in) ? __ldg(p.bias + n0 + i) : 0.f;
-      s_gamma[i] = (p.gamma != nullptr && in) ? __ldg(p.gamma + n0 + i) : 1.f;
-      s_csum[i] = (p.colsum != nullptr && in) ? __ldg(p.colsum + n0 + i) : 0.f;
-    }
-    // fused LayerNorm (consumer): combine the producer's partial sums of this row
-    float ln_mean = 0.f, ln_rstd = 1.f;
-    const bool ln_in = p.stats_in != nullptr;
-    if (ln_in && valid) {
-      float s1 = 0.f, s2 = 0.f;
-      for (int i = 0; i < p.stats_parts_in; ++i) {
-        const float2 q = __ldg(p.stats_in + static_cast<long long>(m) * p.stats_parts_in + i);
-        s1 += q.x;
-        s2 += q.y;
-      }
-      ln_mean = s1 * p.ln_inv_c;
-      ln_rstd = rsqrtf(fmaxf(s2 * p.ln_inv_c - ln_mean * ln_mean, 0.f) + p.ln_eps);
-    }
-    float st_sum = 0.f, st_sq = 0.f;
-    asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_WARPS) : "memory");
-
-    mbar_wait(acc_bar, 0);
-    tc_fence_after();
-    const uint32_t taddr_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
-    const T* resid_row = p.resid != nullptr ? reinterpret_cast<const T*>(p.resid) + res_row * p.ld_resid : nullptr;
     const bool has_gamma = p.gamma != nullptr;
+    const bool ln_in = p.stats_in != nullptr;
     const int act = p.act;
-
-    constexpr int CH_PER_WARP = BN / 16 / (EPI_WARPS / 4);
-#pragma unroll 1
-    for (int c = chalf * CH_PER_WARP; c < (chalf + 1) * CH_PER_WARP; ++c) {
-      const int n = n0 + c * 16;
-      const int nrem = p.N - n;                     // may be <= 0 for the padded tail of the last n-tile
-      const bool full = valid && nrem >= 16;
-      // residual prefetch (independent of the accumulator): issue before waiting on TMEM
-      U8 rr;
-      bool rvec = false;
-      if (full && resid_row != nullptr && (reinterpret_cast<uintptr_t>(resid_row + n) & 31) == 0) {
-        rr = ldg256(resid_row + n);
-        rvec = true;
-      }
-      float v[16];
-      __syncwarp();                                 // tcgen05.ld is .sync.aligned: reconverge first
-      tmem_ld_x16(taddr_row + c * 16, v);
-      tmem_ld_wait();
-      if (!valid || nrem <= 0) continue;
-      if (ln_in) {
-        const float4* sc = reinterpret_cast<const float4*>(s_csum + c * 16);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float4 c4 = sc[j];
-          v[4 * j] = ln_rstd * fmaf(-ln_mean, c4.x, v[4 * j]);
-          v[4 * j + 1] = ln_rstd * fmaf(-ln_mean, c4.y, v[4 * j + 1]);
-          v[4 * j + 2] = ln_rstd * fmaf(-ln_mean, c4.z, v[4 * j + 2]);
-          v[4 * j + 3] = ln_rstd * fmaf(-ln_mean, c4.w, v[4 * j + 3]);
-        }
-      }
-      {
-        const float4* sb = reinterpret_cast<const float4*>(s_bias + c * 16);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float4 b4 = sb[j];
-          v[4 * j] += b4.x; v[4 * j + 1] += b4.y; v[4 * j + 2] += b4.z; v[4 * j + 3] += b4.w;
-        }
-      }
-      if (act == ACT_GELU) {
-#pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] = gelu_erf(v[j]);
-      } else if (act == ACT_RELU) {
-#pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
-      } else if (act == ACT_SILU) {
-#pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] = v[j] / (1.f + __expf(-v[j]));
-      }
-      if (has_gamma) {
-        const float4* sg = reinterpret_cast<const float4*>(s_gamma + c * 16);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float4 g4 = sg[j];
-          v[4 * j] *= g4.x; v[4 * j + 1] *= g4.y; v[4 * j + 2] *= g4.z; v[4 * j + 3] *= g4.w;
-        }
-      }
-      if (rvec) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float2 f = Cvt<T>::unpack(rr.v[j]);
-          v[2 * j] += f.x;
-          v[2 * j + 1] += f.y;
-        }
-      } else if (resid_row != nullptr) {
-        for (int j = 0; j < 16; ++j)
-          if (j < nrem) v[j] += Cvt<T>::to_f(resid_row[n + j]);
-      }
-      // destination
-      long long orow = out_row;
-      int ocol = n;
-      if (p.shuffle_cout > 0) {
-        const int q = n / p.shuffle_cout;
-        ocol = n - q * p.shuffle_cout;
-        orow = (static_cast<long long>(b) * (2 * p.IH) + 2 * y + (q >> 1)) * (2 * p.IW) + 2 * x + (q & 1);
-      }
-      if (p.out_fp32) {
-        float* op = reinterpret_cast<float*>(p.out) + orow * p.ld_out + ocol;
-        if (full && (reinterpret_cast<uintptr_t>(op) & 15) == 0) {
-#pragma unroll
-          for (int j = 0; j < 4; ++j)
-            reinterpret_cast<float4*>(op)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-        } else {
-          for (int j = 0; j < 16; ++j)
-            if (j < nrem) op[j] = v[j];
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const TileCoord tc = decode_tile(p, tile, BN);
+      const int n0 = tc.n0;
+      const int buf = it & 1;
+      int m, b = 0, y = 0, x = 0;
+      bool valid;
+      if (p.a_mode == AMODE_PLAIN) {
+        m = tc.m_tile * BM + r;
+        valid = m < p.M;
+        if (p.remap_rows || p.shuffle_cout) {
+          const int per = p.IH * p.IW;
+          b = m / per;
+          const int rem = m - b * per;
+          if (p.rows_in == ROWS_WINDOW_MAJOR) {
+            const int wh = p.IH >> 2, ww = p.IW >> 2, wsz = wh * ww;
+            const int win = rem / wsz, t = rem - win * wsz;
+            y = (win >> 2) * wh + t / ww;
+            x = (win & 3) * ww + t % ww;
+          } else {
+            y = rem / p.IW;
+            x = rem - y * p.IW;
+          }
         }
       } else {
-        T* op = reinterpret_cast<T*>(p.out) + orow * p.ld_out + ocol;
-        if (full && (reinterpret_cast<uintptr_t>(op) & 31) == 0) {
-          U8 o;
+        const int ry = r / p.TW;
+        y = tc.cy0 + ry;
+        x = tc.cx0 + (r - ry * p.TW);
+        b = tc.cb;
+        valid = (r < p.TW * p.TH) && (y < p.OH) && (x < p.OW);
+        m = (b * p.OH + y) * p.OW + x;
+      }
+      long long out_row = m;
+      if (p.remap_rows) out_row = (static_cast<long long>(b) * p.IH + y) * p.IW + x;
+      const long long res_row = p.resid_mod > 0 ? (m % p.resid_mod) : m;
+
+      // Stage this tile's bias / layer-scale / column-sum vectors in shared memory (double buffered by tile
+      // parity, one named barrier per tile): the per-chunk loop then has no dependent global loads except the
+      // (prefetched) residual.
+      float* s_bias = s_vec + buf * 3 * BN;
+      float* s_gamma = s_bias + BN;
+      float* s_csum = s_gamma + BN;
+      for (int i = threadIdx.x - 64; i < BN; i += 32 * EPI_WARPS) {
+        const bool in = (n0 + i) < p.N;
+        s_bias[i] = (p.bias != nullptr && in) ? __ldg(p.bias + n0 + i) : 0.f;
+        s_gamma[i] = (p.gamma != nullptr && in) ? __ldg(p.gamma + n0 + i) : 1.f;
+        s_csum[i] = (p.colsum != nullptr && in) ? __ldg(p.colsum + n0 + i) : 0.f;
+      }
+      // fused LayerNorm (consumer): combine the producer's partial sums of this row
+      float ln_mean = 0.f, ln_rstd = 1.f;
+      if (ln_in && valid) {
+        float s1 = 0.f, s2 = 0.f;
+        for (int i = 0; i < p.stats_parts_in; ++i) {
+          const float2 q = __ldg(p.stats_in + static_cast<long long>(m) * p.stats_parts_in + i);
+          s1 += q.x;
+          s2 += q.y;
+        }
+        ln_mean = s1 * p.ln_inv_c;
+        ln_rstd = rsqrtf(fmaxf(s2 * p.ln_inv_c - ln_mean * ln_mean, 0.f) + p.ln_eps);
+      }
+      float st_sum = 0.f, st_sq = 0.f;
+      asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_WARPS) : "memory");
+
+      mbar_wait(&acc_full[buf], (it >> 1) & 1);
+      tc_fence_after();
+      const uint32_t taddr_row = tmem_base + buf * ACC_STRIDE + (static_cast<uint32_t>(quarter * 32) << 16);
+      const T* resid_row = p.resid != nullptr ? reinterpret_cast<const T*>(p.resid) + res_row * p.ld_resid : nullptr;
+
+      constexpr int CH_PER_WARP = BN / 16 / (EPI_WARPS / 4);
+#pragma unroll 1
+      for (int c = chalf * CH_PER_WARP; c < (chalf + 1) * CH_PER_WARP; ++c) {
+        const int n = n0 + c * 16;
+        const int nrem = p.N - n;                     // may be <= 0 for the padded tail of the last n-tile
+        const bool full = valid && nrem >= 16;
+        // residual prefetch (independent of the accumulator): issue before waiting on TMEM
+        U8 rr;
+        bool rvec = false;
+        if (full && resid_row != nullptr && (reinterpret_cast<uintptr_t>(resid_row + n) & 31) == 0) {
+          rr = ldg256(resid_row + n);
+          rvec = true;
+        }
+        float v[16];
+        __syncwarp();                                 // tcgen05.ld is .sync.aligned: reconverge first
+        tmem_ld_x16(taddr_row + c * 16, v);
+        tmem_ld_wait();
+        if (!valid || nrem <= 0) continue;
+        if (ln_in) {
+          const float4* sc = reinterpret_cast<const float4*>(s_csum + c * 16);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) o.v[j] = Cvt<T>::pack(v[2 * j], v[2 * j + 1]);
-          stg256(op, o);
-          if (p.stats_out != nullptr) {             // statistics of the ROUNDED values the consumer will read
+          for (int j = 0; j < 4; ++j) {
+            const float4 c4 = sc[j];
+            v[4 * j] = ln_rstd * fmaf(-ln_mean, c4.x, v[4 * j]);
+            v[4 * j + 1] = ln_rstd * fmaf(-ln_mean, c4.y, v[4 * j + 1]);
+            v[4 * j + 2] = ln_rstd * fmaf(-ln_mean, c4.z, v[4 * j + 2]);
+            v[4 * j + 3] = ln_rstd * fmaf(-ln_mean, c4.w, v[4 * j + 3]);
+          }
+        }
+        {
+          const float4* sb = reinterpret_cast<const float4*>(s_bias + c * 16);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float2 f = Cvt<T>::unpack(o.v[j]);
-              st_sum += f.x + f.y;
-              st_sq = fmaf(f.x, f.x, fmaf(f.y, f.y, st_sq));
-            }
+          for (int j = 0; j < 4; ++j) {
+            const float4 b4 = sb[j];
+            v[4 * j] += b4.x; v[4 * j + 1] += b4.y; v[4 * j + 2] += b4.z; v[4 * j + 3] += b4.w;
+          }
+        }
+        if (act == ACT_GELU) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = gelu_erf(v[j]);
+        } else if (act == ACT_RELU) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
+        } else if (act == ACT_SILU) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = v[j] / (1.f + __expf(-v[j]));
+        }
+        if (has_gamma) {
+          const float4* sg = reinterpret_cast<const float4*>(s_gamma + c * 16);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float4 g4 = sg[j];
+            v[4 * j] *= g4.x; v[4 * j + 1] *= g4.y; v[4 * j + 2] *= g4.z; v[4 * j + 3] *= g4.w;
+          }
+        }
+        if (rvec) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float2 f = Cvt<T>::unpack(rr.v[j]);
+            v[2 * j] += f.x;
+            v[2 * j + 1] += f.y;
+          }
+        } else if (resid_row != nullptr) {
+          for (int j = 0; j < 16; ++j)
+            if (j < nrem) v[j] += Cvt<T>::to_f(resid_row[n + j]);
+        }
+        // destination
+        long long orow = out_row;
+        int ocol = n;
+        if (p.shuffle_cout > 0) {
+          const int q = n / p.shuffle_cout;
+          ocol = n - q * p.shuffle_cout;
+          orow = (static_cast<long long>(b) * (2 * p.IH) + 2 * y + (q >> 1)) * (2 * p.IW) + 2 * x + (q & 1);
+        }
+        if (p.out_fp32) {
+          float* op = reinterpret_cast<float*>(p.out) + orow * p.ld_out + ocol;
+          if (full && (reinterpret_cast<uintptr_t>(op) & 15) == 0) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              reinterpret_cast<float4*>(op)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          } else {
+            for (int j = 0; j < 16; ++j)
+              if (j < nrem) op[j] = v[j];
           }
         } else {
-          for (int j = 0; j < 16; ++j)
-            if (j < nrem) {
-              const T h = Cvt<T>::from_f(v[j]);
-              op[j] = h;
-              const float f = Cvt<T>::to_f(h);
-              st_sum += f;
-              st_sq = fmaf(f, f, st_sq);
+          T* op = reinterpret_cast<T*>(p.out) + orow * p.ld_out + ocol;
+          if (full && (reinterpret_cast<uintptr_t>(op) & 31) == 0) {
+            U8 o;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o.v[j] = Cvt<T>::pack(v[2 * j], v[2 * j + 1]);
+            stg256(op, o);
+            if (p.stats_out != nullptr) {             // statistics of the ROUNDED values the consumer will read
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float2 f = Cvt<T>::unpack(o.v[j]);
+                st_sum += f.x + f.y;
+                st_sq = fmaf(f.x, f.x, fmaf(f.y, f.y, st_sq));
+              }
             }
+          } else {
+            for (int j = 0; j < 16; ++j)
+              if (j < nrem) {
+                const T h = Cvt<T>::from_f(v[j]);
+                op[j] = h;
+                const float f = Cvt<T>::to_f(h);
+                st_sum += f;
+                st_sq = fmaf(f, f, st_sq);
+              }
+          }
         }
       }
+      if (p.stats_out != nullptr && valid)
+        p.stats_out[static_cast<long long>(m) * p.stats_parts_out + tc.n_tile * (EPI_WARPS / 4) + chalf] = make_float2(st_sum, st_sq);
+      // release the accumulator buffer to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[buf]);
     }
-    if (p.stats_out != nullptr && valid)
-      p.stats_out[static_cast<long long>(m) * p.stats_parts_out + n_tile * (EPI_WARPS / 4) + chalf] = make_float2(st_sum, st_sq);
-    tc_fence_before();
   }
 
   __syncthreads();
@@ -366,6 +405,15 @@ static int encode(CUtensorMap* tm, int dtype, int rank, const void* base, const 
     return -1;
   }
   return 0;
+}
+
+static int num_sms() {
+  static int n = [] {
+    int dev = 0, v = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = 148;
+    return v;
+  }();
+  return n;
 }
 
 static int pick_bn(int N, int m_tiles) {
@@ -472,12 +520,14 @@ int gemm_build(const GemmDesc& d, GemmOp* op, std::string* err) {
     if (encode(&op->tb, d.dtype, 2, d.W, dims, strides, box, err)) return -1;
   }
   const int stage_bytes = A_STAGE_BYTES + bn * BK * 2;
-  int stages = std::max(2, (100 * 1024) / stage_bytes);
-  stages = std::min(stages, std::max(1, a.kblocks));
-  stages = std::min(stages, 6);
+  int stages = (200 * 1024) / stage_bytes;                 // one persistent CTA per SM: use most of the 227 KB
+  stages = std::min(stages, MAX_STAGES);
+  stages = std::max(2, std::min(stages, std::max(2, 2 * a.kblocks)));
   a.stages = stages;
-  op->smem = 1024 + static_cast<size_t>(stages) * stage_bytes + 128 + 3 * 4 * static_cast<size_t>(bn);
-  op->grid = static_cast<unsigned>(m_tiles) * a.n_tiles;
+  a.m_tiles = m_tiles;
+  op->smem = 1024 + static_cast<size_t>(stages) * stage_bytes + 256 + 2 * 3 * 4 * static_cast<size_t>(bn);
+  const long long tiles = static_cast<long long>(m_tiles) * a.n_tiles;
+  op->grid = static_cast<unsigned>(std::min<long long>(tiles, num_sms()));
   op->flops = 2.0 * d.M * static_cast<double>(d.N) * d.K;
   return 0;
 }
@@ -486,7 +536,7 @@ template <typename T, int BN>
 static int launch_inst(const GemmOp& op, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<T, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<T, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
     if (e != cudaSuccess) return static_cast<int>(e);
     attr_set = true;
   }

@@ -18,7 +18,7 @@ enum : int { ROWS_PLAIN = 0, ROWS_WINDOW_MAJOR = 1 };
 // Device-visible arguments (passed by value to the kernel).
 struct GemmArgs {
   int M, N, kblocks;        // valid rows / valid output columns / K in units of 64
-  int n_tiles, stages;
+  int n_tiles, m_tiles, stages;
   int a_mode;
   uint32_t a_stage_tx;      // bytes TMA delivers into the A slot per stage
   // conv geometry (output grid OH x OW per image, tile TW x TH pixels, Cin/64 channel blocks)
