@@ -1,0 +1,100 @@
+"""Isolated kernel timings for the two kernels BASELINE.json singles out (deformable-attention gather and
+window attention) plus global attention, at the BASELINE configs, through the C ABI.
+
+Timing: CUDA events around each launch, L2 flushed (256 MB write) before every timed launch, median of
+`--iters`; achieved = SURVEY.md 8d algorithmic bytes / time, peak = MEASURED_PEAKS.json HBM copy bandwidth.
+    python tools/bench_kernels.py --out profiles/rNN_kernels.json
+"""
+import argparse
+import json
+import os
+import statistics
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "lw-detr_b200"))
+
+from b200 import capi  # noqa: E402
+from b200.config import CONFIGS  # noqa: E402
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            m = json.load(f)
+        return m["hbm_gbs"], m["bf16_tflops"], "measured"
+    except Exception:
+        return 6650.0, 1590.0, "fallback"
+
+
+def timed(fn, iters, flush):
+    ts = []
+    for _ in range(3):
+        fn()
+    for _ in range(iters):
+        flush.add_(1)                                    # 256 MB read+write evicts the 126 MB L2
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1) * 1e3)
+    return statistics.median(ts), min(ts)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--iters", type=int, default=30)
+    ap.add_argument("--out", default=None)
+    a = ap.parse_args()
+    hbm, tflops, src = peaks()
+    flush = torch.zeros(64 * 1024 * 1024, device="cuda", dtype=torch.float32)
+    res = []
+    g = torch.Generator(device="cuda").manual_seed(0)
+    cases = [("small", 32, torch.float16), ("medium", 64, torch.bfloat16), ("large", 32, torch.float16), ("xlarge", 16, torch.float16)]
+    for name, B, dt in cases:
+        cfg = CONFIGS[name]
+        d, M, L, P, nq, S = cfg.hidden_dim, cfg.ca_nheads, cfg.n_levels, cfg.dec_n_points, cfg.num_queries, cfg.memory_len
+        # ---- deformable attention core (one decoder layer)
+        value = torch.randn(B * S, 3 * d, device="cuda", generator=g).to(dt)
+        ol = (torch.randn(B * nq, 3 * M * L * P, device="cuda", generator=g) * 1.5).to(dt)
+        ref = torch.rand(B * nq, 4, device="cuda", generator=g) * torch.tensor([0.9, 0.9, 0.4, 0.4], device="cuda") + 0.05
+        out = torch.empty(B * nq, d, device="cuda", dtype=dt)
+        fn = lambda: capi.msda_forward(value[:, d:2 * d], ol, ref, out, B, S, nq, M, L, P, list(cfg.level_shapes))
+        med, best = timed(fn, a.iters, flush)
+        elt = 2
+        algo = min(B * S * d, B * nq * M * L * P * 4 * 16) * elt + B * nq * M * L * P * 3 * elt + B * nq * d * elt
+        res.append({"kernel": "msda_forward", "config": "%s B=%d %s" % (name, B, str(dt)[6:]), "us_median": med, "us_best": best,
+                    "algorithmic_MB": algo / 1e6, "achieved_GBps": algo / med / 1e3, "peak_GBps": hbm, "frac": algo / med / 1e3 / hbm, "bound": "hbm"})
+        # ---- ViT attention cores
+        C, heads = cfg.vit_dim, cfg.vit_heads
+        dh = C // heads
+        T = cfg.tokens
+        qkv = torch.randn(B * T, 3 * C, device="cuda", generator=g).to(dt)
+        att = torch.empty(B * T, C, device="cuda", dtype=dt)
+        for kind, nseq, seqlen in (("window_attention", 16 * B, T // 16), ("global_attention", B, T)):
+            fn = lambda: capi.attention(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], att, nseq, seqlen, heads, dh, dh ** -0.5)
+            med, best = timed(fn, a.iters, flush)
+            algo = B * T * 4 * C * elt
+            flops = 4.0 * nseq * seqlen * seqlen * C
+            exps = nseq * heads * seqlen * seqlen
+            r = {"kernel": kind, "config": "%s B=%d %s dh=%d" % (name, B, str(dt)[6:], dh), "us_median": med, "us_best": best,
+                 "algorithmic_MB": algo / 1e6, "achieved_GBps": algo / med / 1e3, "peak_GBps": hbm, "hbm_frac": algo / med / 1e3 / hbm,
+                 "gflop": flops / 1e9, "achieved_TFLOPs": flops / med / 1e6, "tensor_frac": flops / med / 1e6 / tflops,
+                 "gexp_per_s": exps / med / 1e3, "exp_frac_of_mufu_peak": exps / med / 1e3 / (16 * 148 * 1.965)}
+            r["bound"] = "hbm" if kind == "window_attention" else "tensor (nominal) / exp"
+            r["frac"] = r["hbm_frac"] if kind == "window_attention" else r["tensor_frac"]
+            res.append(r)
+        del value, ol, qkv, att
+    for r in res:
+        print(json.dumps(r))
+    if a.out:
+        with open(a.out, "w") as f:
+            json.dump({"peak_source": src, "timing": "CUDA events, L2 flushed before each launch, median of %d" % a.iters, "results": res}, f, indent=1)
+
+
+if __name__ == "__main__":
+    main()
