@@ -12,6 +12,8 @@
 #include "attn.h"
 #include "ptx.cuh"
 
+#include <algorithm>
+
 namespace lwb {
 
 template <typename T> struct Mma;
@@ -58,6 +60,96 @@ __device__ __forceinline__ float fast_exp2(float x) {
 
 static constexpr int KC = 64;      // keys per shared-memory chunk
 static constexpr int NSTAGE = 3;   // K/V ring: chunk ch+2 is prefetched while ch is consumed -> one barrier per chunk
+
+// One 64-key chunk of the online-softmax attention for a warp's 16 query rows.
+//   qf: Q fragments (A operand); cK / cV: the chunk's K and V rows in shared memory ([64][LDS]);
+//   kbase: index of the chunk's first key; keys >= seqlen are masked.
+template <typename T, int DH>
+__device__ __forceinline__ void attn_chunk(const uint32_t (&qf)[DH / 16][4], const T* cK, const T* cV, int kbase, int seqlen,
+                                           float scale_log2, int lane, float (&m_run)[2], float (&lsum)[4],
+                                           float (&o)[DH / 8][4]) {
+  constexpr int LDS = DH + 8;
+  const int t4 = lane & 3;
+  const uint32_t ones2 = Cvt<T>::pack(1.f, 1.f);
+    // ---- S = Q K^T for 64 keys: 8 n-tiles of 8 keys
+    float s[KC / 8][4];
+#pragma unroll
+    for (int nt = 0; nt < KC / 8; ++nt) s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
+#pragma unroll
+    for (int nt = 0; nt < KC / 8; nt += 2) {
+#pragma unroll
+      for (int kk = 0; kk < DH / 16; ++kk) {
+        // x4 = (keys nt*8.., dh lo), (keys nt*8.., dh hi), (keys (nt+1)*8.., dh lo), (keys (nt+1)*8.., dh hi)
+        uint32_t kf[4];
+        const int key = (nt + (lane >> 4)) * 8 + (lane & 7);
+        const int c = kk * 16 + ((lane >> 3) & 1) * 8;
+        ldsm_x4(kf, smem_u32(cK + key * LDS + c));
+        Mma<T>::run(s[nt], qf[kk], kf[0], kf[1]);
+        Mma<T>::run(s[nt + 1], qf[kk], kf[2], kf[3]);
+      }
+    }
+    // ---- online softmax.  Instruction diet (the kernel is MUFU/issue bound at dh = 16): the max runs on the
+    // raw scores, scale and max-subtraction are one FFMA feeding ex2, tail masking only touches the last
+    // chunk, and the row sums come from one extra MMA against a ones fragment (below) instead of FADDs.
+    if (kbase + KC > seqlen) {
+#pragma unroll
+      for (int nt = 0; nt < KC / 8; ++nt)
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (kbase + nt * 8 + t4 * 2 + (j & 1) >= seqlen) s[nt][j] = -INFINITY;
+    }
+    float mx[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+    for (int nt = 0; nt < KC / 8; ++nt) {
+      mx[0] = fmaxf(mx[0], fmaxf(s[nt][0], s[nt][1]));
+      mx[1] = fmaxf(mx[1], fmaxf(s[nt][2], s[nt][3]));
+    }
+    float alpha[2], msc[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      mx[h] = fmaxf(mx[h], __shfl_xor_sync(0xffffffffu, mx[h], 1));
+      mx[h] = fmaxf(mx[h], __shfl_xor_sync(0xffffffffu, mx[h], 2));
+      const float m_new = fmaxf(m_run[h], mx[h]);            // running max of the RAW scores
+      alpha[h] = fast_exp2((m_run[h] - m_new) * scale_log2);
+      m_run[h] = m_new;
+      msc[h] = m_new * scale_log2;
+    }
+    uint32_t pf[KC / 16][4];
+#pragma unroll
+    for (int nt = 0; nt < KC / 8; ++nt) {
+      const float p0 = fast_exp2(fmaf(s[nt][0], scale_log2, -msc[0]));
+      const float p1 = fast_exp2(fmaf(s[nt][1], scale_log2, -msc[0]));
+      const float p2 = fast_exp2(fmaf(s[nt][2], scale_log2, -msc[1]));
+      const float p3 = fast_exp2(fmaf(s[nt][3], scale_log2, -msc[1]));
+      // C fragments of n-tiles (2j, 2j+1) form the A fragment of key-step j
+      pf[nt >> 1][(nt & 1) * 2 + 0] = Cvt<T>::pack(p0, p1);
+      pf[nt >> 1][(nt & 1) * 2 + 1] = Cvt<T>::pack(p2, p3);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) lsum[j] *= alpha[j >> 1];
+#pragma unroll
+    for (int dt = 0; dt < DH / 8; ++dt) {
+      o[dt][0] *= alpha[0];
+      o[dt][1] *= alpha[0];
+      o[dt][2] *= alpha[1];
+      o[dt][3] *= alpha[1];
+    }
+    // ---- O += P V
+#pragma unroll
+    for (int kt = 0; kt < KC / 16; ++kt) {
+      Mma<T>::run(lsum, pf[kt], ones2, ones2);               // row sums of the rounded P, fp32 accumulate
+#pragma unroll
+      for (int dt = 0; dt < DH / 8; dt += 2) {
+        // trans x4 = (keys 0-7, dh dt), (keys 8-15, dh dt), (keys 0-7, dh dt+1), (keys 8-15, dh dt+1)
+        uint32_t vf[4];
+        const int key = kt * 16 + (lane & 15);
+        const int c = (dt + (lane >> 4)) * 8;
+        ldsm_x4_t(vf, smem_u32(cV + key * LDS + c));
+        Mma<T>::run(o[dt], pf[kt], vf[0], vf[1]);
+        Mma<T>::run(o[dt + 1], pf[kt], vf[2], vf[3]);
+      }
+    }
+}
 
 template <typename T, int DH, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32) attn_kernel(const AttnArgs p) {
@@ -106,7 +198,6 @@ __global__ void __launch_bounds__(WARPS * 32) attn_kernel(const AttnArgs p) {
   for (int i = 0; i < DH / 8; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
   float m_run[2] = {-INFINITY, -INFINITY};
   float lsum[4] = {0.f, 0.f, 0.f, 0.f};                      // [row g | row g | row g+8 | row g+8] sums of P
-  const uint32_t ones2 = Cvt<T>::pack(1.f, 1.f);
   const int g = lane >> 2, t4 = lane & 3;
 
   for (int ch = 0; ch < nchunks; ++ch) {
@@ -127,85 +218,7 @@ __global__ void __launch_bounds__(WARPS * 32) attn_kernel(const AttnArgs p) {
     const T* cK = sK + buf * KC * LDS;
     const T* cV = sV + buf * KC * LDS;
 
-    // ---- S = Q K^T for 64 keys: 8 n-tiles of 8 keys
-    float s[KC / 8][4];
-#pragma unroll
-    for (int nt = 0; nt < KC / 8; ++nt) s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
-#pragma unroll
-    for (int nt = 0; nt < KC / 8; nt += 2) {
-#pragma unroll
-      for (int kk = 0; kk < DH / 16; ++kk) {
-        // x4 = (keys nt*8.., dh lo), (keys nt*8.., dh hi), (keys (nt+1)*8.., dh lo), (keys (nt+1)*8.., dh hi)
-        uint32_t kf[4];
-        const int key = (nt + (lane >> 4)) * 8 + (lane & 7);
-        const int c = kk * 16 + ((lane >> 3) & 1) * 8;
-        ldsm_x4(kf, smem_u32(cK + key * LDS + c));
-        Mma<T>::run(s[nt], qf[kk], kf[0], kf[1]);
-        Mma<T>::run(s[nt + 1], qf[kk], kf[2], kf[3]);
-      }
-    }
-    // ---- online softmax.  Instruction diet (the kernel is MUFU/issue bound at dh = 16): the max runs on the
-    // raw scores, scale and max-subtraction are one FFMA feeding ex2, tail masking only touches the last
-    // chunk, and the row sums come from one extra MMA against a ones fragment (below) instead of FADDs.
-    const int kbase = ch * KC;
-    if (kbase + KC > p.seqlen) {
-#pragma unroll
-      for (int nt = 0; nt < KC / 8; ++nt)
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-          if (kbase + nt * 8 + t4 * 2 + (j & 1) >= p.seqlen) s[nt][j] = -INFINITY;
-    }
-    float mx[2] = {-INFINITY, -INFINITY};
-#pragma unroll
-    for (int nt = 0; nt < KC / 8; ++nt) {
-      mx[0] = fmaxf(mx[0], fmaxf(s[nt][0], s[nt][1]));
-      mx[1] = fmaxf(mx[1], fmaxf(s[nt][2], s[nt][3]));
-    }
-    float alpha[2], msc[2];
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      mx[h] = fmaxf(mx[h], __shfl_xor_sync(0xffffffffu, mx[h], 1));
-      mx[h] = fmaxf(mx[h], __shfl_xor_sync(0xffffffffu, mx[h], 2));
-      const float m_new = fmaxf(m_run[h], mx[h]);            // running max of the RAW scores
-      alpha[h] = fast_exp2((m_run[h] - m_new) * p.scale_log2);
-      m_run[h] = m_new;
-      msc[h] = m_new * p.scale_log2;
-    }
-    uint32_t pf[KC / 16][4];
-#pragma unroll
-    for (int nt = 0; nt < KC / 8; ++nt) {
-      const float p0 = fast_exp2(fmaf(s[nt][0], p.scale_log2, -msc[0]));
-      const float p1 = fast_exp2(fmaf(s[nt][1], p.scale_log2, -msc[0]));
-      const float p2 = fast_exp2(fmaf(s[nt][2], p.scale_log2, -msc[1]));
-      const float p3 = fast_exp2(fmaf(s[nt][3], p.scale_log2, -msc[1]));
-      // C fragments of n-tiles (2j, 2j+1) form the A fragment of key-step j
-      pf[nt >> 1][(nt & 1) * 2 + 0] = Cvt<T>::pack(p0, p1);
-      pf[nt >> 1][(nt & 1) * 2 + 1] = Cvt<T>::pack(p2, p3);
-    }
-#pragma unroll
-    for (int j = 0; j < 4; ++j) lsum[j] *= alpha[j >> 1];
-#pragma unroll
-    for (int dt = 0; dt < DH / 8; ++dt) {
-      o[dt][0] *= alpha[0];
-      o[dt][1] *= alpha[0];
-      o[dt][2] *= alpha[1];
-      o[dt][3] *= alpha[1];
-    }
-    // ---- O += P V
-#pragma unroll
-    for (int kt = 0; kt < KC / 16; ++kt) {
-      Mma<T>::run(lsum, pf[kt], ones2, ones2);               // row sums of the rounded P, fp32 accumulate
-#pragma unroll
-      for (int dt = 0; dt < DH / 8; dt += 2) {
-        // trans x4 = (keys 0-7, dh dt), (keys 8-15, dh dt), (keys 0-7, dh dt+1), (keys 8-15, dh dt+1)
-        uint32_t vf[4];
-        const int key = kt * 16 + (lane & 15);
-        const int c = (dt + (lane >> 4)) * 8;
-        ldsm_x4_t(vf, smem_u32(cV + key * LDS + c));
-        Mma<T>::run(o[dt], pf[kt], vf[0], vf[1]);
-        Mma<T>::run(o[dt + 1], pf[kt], vf[2], vf[3]);
-      }
-    }
+    attn_chunk<T, DH>(qf, cK, cV, ch * KC, p.seqlen, p.scale_log2, lane, m_run, lsum, o);
   }
 
   // ---- finalise: divide by the row sums, stage through this warp's Q rows, 16-byte coalesced stores
@@ -227,6 +240,117 @@ __global__ void __launch_bounds__(WARPS * 32) attn_kernel(const AttnArgs p) {
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Short sequences (seqlen <= 112, i.e. the 10x10 ViT windows): one work item = one (sequence, head), whose
+// whole Q / K / V (<= 128 rows) fits one shared-memory buffer.  A per-item CTA spends most of its life waiting
+// for its only loads, so here persistent CTAs walk items  blockIdx.x, +gridDim.x, ...  (head fastest: the CTAs
+// running at the same time read neighbouring 32..128-byte slices of the same token rows) and prefetch item
+// i+2 into a 3-deep buffer ring while item i is computed - the HBM latency is hidden behind the math and the
+// kernel runs at the larger of its HBM time and its exp (MUFU) time.
+template <typename T, int DH>
+__global__ void __launch_bounds__(7 * 32) attn_short_kernel(const AttnArgs p) {
+  constexpr int WARPS = 7, QROWS = 112, KROWS = 128, NBUF = 3;
+  constexpr int LDS = DH + 8, CPR = DH / 8;
+  constexpr int BUF_ELEMS = (QROWS + 2 * KROWS) * LDS;
+  extern __shared__ __align__(16) uint8_t smem_attn[];
+  T* sbase = reinterpret_cast<T*>(smem_attn);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, t4 = lane & 3;
+  const long long nitems = static_cast<long long>(p.nseq) * p.heads;
+
+  auto issue_loads = [&](long long item, int buf) {
+    const int head = static_cast<int>(item % p.heads);
+    const long long row_base = (item / p.heads) * p.seqlen;
+    T* sQ = sbase + buf * BUF_ELEMS;
+    T* sK = sQ + QROWS * LDS;
+    T* sV = sK + KROWS * LDS;
+    const T* gq = reinterpret_cast<const T*>(p.q) + head * DH;
+    const T* gk = reinterpret_cast<const T*>(p.k) + head * DH;
+    const T* gv = reinterpret_cast<const T*>(p.v) + head * DH;
+    for (int i = tid; i < KROWS * CPR; i += WARPS * 32) {
+      const int r = i / CPR, c = i % CPR;
+      const bool ok = r < p.seqlen;
+      const long long row = row_base + (ok ? r : 0);
+      if (r < QROWS) cp_async16(smem_u32(sQ + r * LDS + c * 8), gq + row * p.ldq + c * 8, ok);
+      cp_async16(smem_u32(sK + r * LDS + c * 8), gk + row * p.ldk + c * 8, ok);
+      cp_async16(smem_u32(sV + r * LDS + c * 8), gv + row * p.ldv + c * 8, ok);
+    }
+  };
+
+  long long item = blockIdx.x;
+  if (item < nitems) issue_loads(item, 0);
+  cp_async_commit();
+  if (item + gridDim.x < nitems) issue_loads(item + gridDim.x, 1);
+  cp_async_commit();
+
+  for (int it = 0; item < nitems; item += gridDim.x, ++it) {
+    const int buf = it % NBUF;
+    cp_async_wait<1>();                    // this item's group has landed
+    __syncthreads();                       // ... for all threads; everyone is also done with item it-1
+    if (item + 2LL * gridDim.x < nitems) issue_loads(item + 2LL * gridDim.x, (it + 2) % NBUF);
+    cp_async_commit();
+
+    T* sQ = sbase + buf * BUF_ELEMS;
+    const T* sK = sQ + QROWS * LDS;
+    const T* sV = sK + KROWS * LDS;
+    uint32_t qf[DH / 16][4];
+#pragma unroll
+    for (int kk = 0; kk < DH / 16; ++kk) {
+      const int r = warp * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
+      const int c = kk * 16 + (lane >> 4) * 8;
+      ldsm_x4(qf[kk], smem_u32(sQ + r * LDS + c));
+    }
+    float o[DH / 8][4];
+#pragma unroll
+    for (int i = 0; i < DH / 8; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
+    float m_run[2] = {-INFINITY, -INFINITY};
+    float lsum[4] = {0.f, 0.f, 0.f, 0.f};
+    attn_chunk<T, DH>(qf, sK, sV, 0, p.seqlen, p.scale_log2, lane, m_run, lsum, o);
+    if (p.seqlen > KC) attn_chunk<T, DH>(qf, sK + KC * LDS, sV + KC * LDS, KC, p.seqlen, p.scale_log2, lane, m_run, lsum, o);
+
+    const float l_run[2] = {1.f / lsum[0], 1.f / lsum[2]};
+    T* sO = sQ + warp * 16 * LDS;          // this warp's own Q rows: already consumed into qf
+    __syncwarp();
+#pragma unroll
+    for (int dt = 0; dt < DH / 8; ++dt) {
+      *reinterpret_cast<uint32_t*>(sO + g * LDS + dt * 8 + t4 * 2) = Cvt<T>::pack(o[dt][0] * l_run[0], o[dt][1] * l_run[0]);
+      *reinterpret_cast<uint32_t*>(sO + (g + 8) * LDS + dt * 8 + t4 * 2) = Cvt<T>::pack(o[dt][2] * l_run[1], o[dt][3] * l_run[1]);
+    }
+    __syncwarp();
+    const int head = static_cast<int>(item % p.heads);
+    const long long row_base = (item / p.heads) * p.seqlen;
+    T* go = reinterpret_cast<T*>(p.o) + head * DH;
+    for (int i = lane; i < 16 * CPR; i += 32) {
+      const int r = i / CPR, c = i % CPR;
+      const int qrow = warp * 16 + r;
+      if (qrow < p.seqlen)
+        *reinterpret_cast<U4*>(go + (row_base + qrow) * p.ldo + c * 8) = *reinterpret_cast<const U4*>(sO + r * LDS + c * 8);
+    }
+  }
+}
+
+template <typename T, int DH>
+static int launch_short(const AttnArgs& a, cudaStream_t st) {
+  constexpr int LDS = DH + 8;
+  const size_t smem = static_cast<size_t>(3) * (112 + 256) * LDS * sizeof(T);
+  static int ctas_per_sm = 0;
+  if (!ctas_per_sm) {
+    cudaError_t e = cudaFuncSetAttribute(attn_short_kernel<T, DH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    int n = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, attn_short_kernel<T, DH>, 7 * 32, smem);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    ctas_per_sm = n > 0 ? n : 1;
+  }
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const long long items = static_cast<long long>(a.nseq) * a.heads;
+  const unsigned grid = static_cast<unsigned>(std::min<long long>(items, static_cast<long long>(sms) * ctas_per_sm));
+  attn_short_kernel<T, DH><<<grid, 7 * 32, smem, st>>>(a);
+  return static_cast<int>(cudaGetLastError());
+}
+
 template <typename T, int DH, int WARPS>
 static int launch(const AttnArgs& a, cudaStream_t st) {
   constexpr int LDS = DH + 8;
@@ -244,11 +368,17 @@ static int launch(const AttnArgs& a, cudaStream_t st) {
 
 template <typename T>
 static int dispatch(const AttnArgs& a, int dh, cudaStream_t st) {
-  const int warps = a.seqlen <= 112 ? 7 : (a.seqlen >= 1024 ? 8 : 4);
+  if (a.seqlen <= 112) {
+    if (dh == 16) return launch_short<T, 16>(a, st);
+    if (dh == 32) return launch_short<T, 32>(a, st);
+    if (dh == 64) return launch_short<T, 64>(a, st);
+    return -2;
+  }
+  const int warps = a.seqlen >= 1024 ? 8 : 4;
 #define LWB_ATTN_CASE(D, W) if (dh == D && warps == W) return launch<T, D, W>(a, st);
-  LWB_ATTN_CASE(16, 7) LWB_ATTN_CASE(16, 8) LWB_ATTN_CASE(16, 4)
-  LWB_ATTN_CASE(32, 7) LWB_ATTN_CASE(32, 8) LWB_ATTN_CASE(32, 4)
-  LWB_ATTN_CASE(64, 7) LWB_ATTN_CASE(64, 8) LWB_ATTN_CASE(64, 4)
+  LWB_ATTN_CASE(16, 8) LWB_ATTN_CASE(16, 4)
+  LWB_ATTN_CASE(32, 8) LWB_ATTN_CASE(32, 4)
+  LWB_ATTN_CASE(64, 8) LWB_ATTN_CASE(64, 4)
 #undef LWB_ATTN_CASE
   return -2;
 }

@@ -57,7 +57,28 @@ __device__ __forceinline__ TileCoord decode_tile(const GemmArgs& p, int tile, in
   return t;
 }
 
-// Persistent: one CTA per SM walks tiles blockIdx.x, +gridDim.x, ...  The smem ring (TMA -> MMA) runs
+// Tile walk of a persistent CTA.  Streaming mode: tiles blockIdx.x, +gridDim.x, ... (n fastest).
+// W-stationary mode (small K): the CTA owns ONE n-tile (its W slice stays resident in shared memory) and
+// walks m-tiles  blockIdx.x / n_tiles,  + gridDim.x / n_tiles, ...  - CTAs c, c+1, .. of one m-group work on
+// the same A rows at the same time, so A is fetched from HBM once and re-read from L2.
+struct TileWalk {
+  int tile, step, end;
+  __device__ __forceinline__ TileWalk(const GemmArgs& p) {
+    if (p.w_stationary) {
+      const int groups = gridDim.x / p.n_tiles;
+      tile = (blockIdx.x / p.n_tiles) * p.n_tiles + (blockIdx.x % p.n_tiles);
+      step = groups * p.n_tiles;
+    } else {
+      tile = blockIdx.x;
+      step = gridDim.x;
+    }
+    end = p.m_tiles * p.n_tiles;
+  }
+  __device__ __forceinline__ bool valid() const { return tile < end; }
+  __device__ __forceinline__ void next() { tile += step; }
+};
+
+// Persistent: one CTA per SM walks its tiles (see TileWalk).  The smem ring (TMA -> MMA) runs
 // continuously across tiles and the accumulator is double buffered in TMEM, so the epilogue of tile i
 // overlaps the loads and MMAs of tile i+1.
 template <typename T, int BN>
@@ -71,11 +92,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int stages = p.stages;
   uint8_t* sA = smem;
   uint8_t* sB = smem + stages * A_STAGE_BYTES;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sB + stages * B_STAGE_BYTES);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sB + p.b_slots * B_STAGE_BYTES);
   uint64_t* empty_bar = full_bar + MAX_STAGES;
   uint64_t* acc_full = empty_bar + MAX_STAGES;      // [2]
   uint64_t* acc_empty = acc_full + 2;               // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  uint64_t* w_bar = acc_empty + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_bar + 1);
   float* s_vec = reinterpret_cast<float*>(full_bar + 32);   // 256 B of barriers, then 2 x {bias | gamma | colsum}[BN]
 
   const int warp = threadIdx.x >> 5;
@@ -93,6 +115,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       mbar_init(&acc_full[b], 1);
       mbar_init(&acc_empty[b], EPI_WARPS);
     }
+    mbar_init(w_bar, 1);
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -108,13 +131,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (lane == 0) {
       // ------------------------------------------------------------------ TMA producer
       uint32_t ring = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const TileCoord tc = decode_tile(p, tile, BN);
+      if (p.w_stationary) {
+        // the CTA's n-tile of W (all of K) is loaded once and stays resident
+        const TileCoord tc = decode_tile(p, TileWalk(p).tile < num_tiles ? TileWalk(p).tile : 0, BN);
+        mbar_arrive_expect_tx(w_bar, static_cast<uint32_t>(p.kblocks) * B_STAGE_BYTES);
+        for (int kb = 0; kb < p.kblocks; ++kb) tma_load_2d(sB + kb * B_STAGE_BYTES, &tmB, w_bar, kb * BK, tc.n0);
+      }
+      for (TileWalk tw(p); tw.valid(); tw.next()) {
+        const TileCoord tc = decode_tile(p, tw.tile, BN);
         for (int kb = 0; kb < p.kblocks; ++kb, ++ring) {
           const int s = ring % stages;
           const uint32_t ph = (ring / stages) & 1;
           mbar_wait(&empty_bar[s], ph ^ 1);
-          mbar_arrive_expect_tx(&full_bar[s], p.a_stage_tx + B_STAGE_BYTES);
+          mbar_arrive_expect_tx(&full_bar[s], p.a_stage_tx + (p.w_stationary ? 0u : static_cast<uint32_t>(B_STAGE_BYTES)));
           uint8_t* a_dst = sA + s * A_STAGE_BYTES;
           if (p.a_mode == AMODE_PLAIN) {
             tma_load_2d(a_dst, &tmA, &full_bar[s], kb * BK, tc.m_tile * BM);
@@ -131,7 +160,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               tma_load_5d(a_dst, &tmA, &full_bar[s], px * p.lda + c0, tc.cx0 + xoff, py, tc.cy0 + yoff, tc.cb);
             }
           }
-          tma_load_2d(sB + s * B_STAGE_BYTES, &tmB, &full_bar[s], kb * BK, tc.n0);
+          if (!p.w_stationary) tma_load_2d(sB + s * B_STAGE_BYTES, &tmB, &full_bar[s], kb * BK, tc.n0);
         }
       }
     }
@@ -141,7 +170,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       constexpr uint32_t idesc = umma_idesc_f16(Cvt<T>::is_bf16, BM, BN);
       uint32_t ring = 0;
       int it = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      if (p.w_stationary) mbar_wait(w_bar, 0);
+      for (TileWalk tw(p); tw.valid(); tw.next(), ++it) {
         const int buf = it & 1;
         mbar_wait(&acc_empty[buf], ((it >> 1) & 1) ^ 1);     // epilogue has drained this accumulator buffer
         tc_fence_after();
@@ -152,7 +182,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           mbar_wait(&full_bar[s], ph);
           tc_fence_after();
           const uint64_t adesc = umma_desc_k128(smem_u32(sA + s * A_STAGE_BYTES));
-          const uint64_t bdesc = umma_desc_k128(smem_u32(sB + s * B_STAGE_BYTES));
+          const uint64_t bdesc = umma_desc_k128(smem_u32(sB + (p.w_stationary ? kb : s) * B_STAGE_BYTES));
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
             // advance 16 elements (32 B) along K inside the 128 B swizzle row: +2 in 16-byte units
@@ -172,8 +202,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const bool ln_in = p.stats_in != nullptr;
     const int act = p.act;
     int it = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-      const TileCoord tc = decode_tile(p, tile, BN);
+    for (TileWalk tw(p); tw.valid(); tw.next(), ++it) {
+      const TileCoord tc = decode_tile(p, tw.tile, BN);
       const int n0 = tc.n0;
       const int buf = it & 1;
       int m, b = 0, y = 0, x = 0;
@@ -519,15 +549,29 @@ int gemm_build(const GemmDesc& d, GemmOp* op, std::string* err) {
     const cuuint32_t box[2] = {BK, static_cast<cuuint32_t>(bn)};
     if (encode(&op->tb, d.dtype, 2, d.W, dims, strides, box, err)) return -1;
   }
-  const int stage_bytes = A_STAGE_BYTES + bn * BK * 2;
-  int stages = (200 * 1024) / stage_bytes;                 // one persistent CTA per SM: use most of the 227 KB
+  const int b_stage = bn * BK * 2;
+  const int budget = 200 * 1024;
+  // W-stationary when the CTA's whole W slice (all of K) fits beside a useful A ring
+  const bool wstat = d.a_mode == AMODE_PLAIN && static_cast<long long>(a.kblocks) * b_stage <= 150 * 1024 &&
+                     static_cast<long long>(m_tiles) * a.n_tiles >= 2LL * num_sms();
+  int stages;
+  if (wstat) {
+    stages = (budget - a.kblocks * b_stage) / A_STAGE_BYTES;
+    a.b_slots = a.kblocks;
+  } else {
+    stages = budget / (A_STAGE_BYTES + b_stage);
+  }
   stages = std::min(stages, MAX_STAGES);
   stages = std::max(2, std::min(stages, std::max(2, 2 * a.kblocks)));
+  if (!wstat) a.b_slots = stages;
+  a.w_stationary = wstat ? 1 : 0;
   a.stages = stages;
   a.m_tiles = m_tiles;
-  op->smem = 1024 + static_cast<size_t>(stages) * stage_bytes + 256 + 2 * 3 * 4 * static_cast<size_t>(bn);
+  op->smem = 1024 + static_cast<size_t>(stages) * A_STAGE_BYTES + static_cast<size_t>(a.b_slots) * b_stage + 256 + 2 * 3 * 4 * static_cast<size_t>(bn);
   const long long tiles = static_cast<long long>(m_tiles) * a.n_tiles;
-  op->grid = static_cast<unsigned>(std::min<long long>(tiles, num_sms()));
+  long long grid = std::min<long long>(tiles, num_sms());
+  if (wstat) grid = std::max<long long>(a.n_tiles, (num_sms() / a.n_tiles) * a.n_tiles);
+  op->grid = static_cast<unsigned>(grid);
   op->flops = 2.0 * d.M * static_cast<double>(d.N) * d.K;
   return 0;
 }
