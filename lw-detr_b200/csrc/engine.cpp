@@ -438,7 +438,7 @@ int Engine::plan(int B, std::string* err) {
       if (fail || gemm_build(g, &op, &e)) { if (!fail) *err = label + ": " + e; fail = true; return; }
       if (o.stats_out) {
         if (stats_parts == 0) stats_parts = op.args.stats_parts_out;
-        if (stats_parts != op.args.stats_parts_out || stats_parts > 24) { *err = label + ": inconsistent LayerNorm partial count"; fail = true; return; }
+        if (stats_parts != op.args.stats_parts_out || stats_parts > 48) { *err = label + ": inconsistent LayerNorm partial count"; fail = true; return; }
       }
       Op P_;
       P_.label = label;
@@ -500,8 +500,8 @@ int Engine::plan(int B, std::string* err) {
       add_op("patch_gather", [this, a0p, B, img, dt](cudaStream_t st) { return patch_gather_launch(dt, in_images_, in_images_fp32_, a0p, B, img, st); },
              a0.p, BT, 768, 768, 0, 1.0 * B * 3 * img * img * 4 + 2.0 * BT * 768);
     }
-    float2* stats_x = static_cast<float2*>(salloc(static_cast<size_t>(BT) * 24 * sizeof(float2)));   // row stats of x (block input)
-    float2* stats_m = static_cast<float2*>(salloc(static_cast<size_t>(BT) * 24 * sizeof(float2)));   // row stats of x + attn
+    float2* stats_x = static_cast<float2*>(salloc(static_cast<size_t>(BT) * 48 * sizeof(float2)));   // row stats of x (block input)
+    float2* stats_m = static_cast<float2*>(salloc(static_cast<size_t>(BT) * 48 * sizeof(float2)));   // row stats of x + attn
     const bool fuse = fuse_ln_ != 0;
     Mat xcur = xa;
     {

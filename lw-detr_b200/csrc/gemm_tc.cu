@@ -1,13 +1,14 @@
 // tcgen05 / TMA GEMM family (see gemm_tc.h).  Persistent CTAs (one per SM) compute 128 x BN output tiles:
 //   warp 0 : TMA producer (one elected lane) - fills a ring of {A 128x64, W BNx64} stages
 //   warp 1 : TMEM allocator + tcgen05.mma issuer (one elected lane), accumulator in TMEM
-//   warps 2-9 : epilogue, two warps per TMEM lane quarter: tcgen05.ld -> bias/act/layer-scale/residual ->
+//   warps 2-17: epilogue, four warps per TMEM lane quarter: tcgen05.ld -> bias/act/layer-scale/residual ->
 //               16-bit (or fp32) rows to global, with optional row re-ordering / pixel shuffle.
 // Replaces, on the LW-DETR path, every F.linear / nn.Conv2d / nn.ConvTranspose2d call listed in
 // SURVEY.md appendix B (reference: models/backbone/vit.py:120-140,206-220, projector.py:85-132,
 // transformer.py:27-39,466-517, ops/modules/ms_deform_attn.py:112-143, lwdetr.py:149-159).
 #include "gemm_tc.h"
 #include "ptx.cuh"
+#include "tma_util.h"
 
 #include <algorithm>
 #include <cstdio>
@@ -18,7 +19,7 @@ namespace lwb {
 static constexpr int BM = 128;
 static constexpr int BK = 64;
 static constexpr int A_STAGE_BYTES = BM * BK * 2;
-static constexpr int EPI_WARPS = 8;                       // two warps per TMEM lane quarter, half of the columns each
+static constexpr int EPI_WARPS = 16;                      // four warps per TMEM lane quarter, a quarter of the columns each
 static constexpr int GEMM_THREADS = 64 + 32 * EPI_WARPS;
 static constexpr int MAX_STAGES = 8;
 
@@ -196,7 +197,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   } else {
     // -------------------------------------------------------------------- epilogue (8 warps)
     const int quarter = warp & 3;               // TMEM lanes [32*quarter, 32*quarter+32) (hardware: warp_id % 4)
-    const int chalf = (warp - 2) >> 2;          // which half of the tile's 16-column chunks this warp owns
+    const int chalf = (warp - 2) >> 2;          // which slice of the tile's 16-column chunks this warp owns
     const int r = quarter * 32 + lane;          // row inside the tile
     const bool has_gamma = p.gamma != nullptr;
     const bool ln_in = p.stats_in != nullptr;
@@ -397,44 +398,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 }
 
 // ------------------------------------------------------------------------------------------- host
-typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                        const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
-                                        CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
-                                        CUtensorMapFloatOOBfill);
-
-static PFN_tmapEncodeTiled encode_fn() {
-  static PFN_tmapEncodeTiled fn = [] {
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
-        q != cudaDriverEntryPointSuccess)
-      p = nullptr;
-    return reinterpret_cast<PFN_tmapEncodeTiled>(p);
-  }();
-  return fn;
-}
-
 static int encode(CUtensorMap* tm, int dtype, int rank, const void* base, const cuuint64_t* dims,
                   const cuuint64_t* strides_bytes, const cuuint32_t* box, std::string* err) {
-  PFN_tmapEncodeTiled fn = encode_fn();
-  if (!fn) {
-    *err = "cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)";
-    return -1;
-  }
-  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-  CUresult r = fn(tm, dtype == DT_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16,
-                  static_cast<cuuint32_t>(rank), const_cast<void*>(base), dims, strides_bytes, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) {
-    char buf[256];
-    snprintf(buf, sizeof buf, "cuTensorMapEncodeTiled failed (CUresult %d, rank %d, dim0 %llu, stride1 %llu, box0 %u)",
-             static_cast<int>(r), rank, (unsigned long long)dims[0],
-             (unsigned long long)(rank > 1 ? strides_bytes[0] : 0), box[0]);
-    *err = buf;
-    return -1;
-  }
-  return 0;
+  return tma_encode(tm, dtype, rank, base, dims, strides_bytes, box, 128, err);
 }
 
 static int num_sms() {

@@ -22,7 +22,7 @@ __device__ __forceinline__ U4 ldg_nc16(const void* p) {
 }
 
 template <typename T, int NL, int NP>   // levels, points per head and level
-__global__ void __launch_bounds__(256) msda_fwd_kernel(const MsdaArgs p) {
+__global__ void __launch_bounds__(256, (NL * NP <= 2) ? 8 : ((NL * NP <= 4) ? 6 : 4)) msda_fwd_kernel(const MsdaArgs p) {
   constexpr int D = 16;
   constexpr int LP = NL * NP;
   const long long gid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
