@@ -1,8 +1,13 @@
-// tcgen05 / TMA GEMM family (see gemm_tc.h).  Persistent CTAs (one per SM) compute 128 x BN output tiles:
-//   warp 0 : TMA producer (one elected lane) - fills a ring of {A 128x64, W BNx64} stages
-//   warp 1 : TMEM allocator + tcgen05.mma issuer (one elected lane), accumulator in TMEM
-//   warps 2-17: epilogue, four warps per TMEM lane quarter: tcgen05.ld -> bias/act/layer-scale/residual ->
-//               16-bit (or fp32) rows to global, with optional row re-ordering / pixel shuffle.
+// tcgen05 / TMA GEMM family (see gemm_tc.h).  Persistent CTA PAIRS (clusters of 2, one pair per two SMs)
+// compute 256 x BN output tiles with tcgen05.mma.cta_group::2 - a single-CTA tcgen05.mma was measured at about
+// half of the pair rate on this part (profiles/r01c_gemm_timeline.txt), so every GEMM of the path runs paired:
+//   warp 0   : TMA producer (one elected lane, in BOTH CTAs): its CTA's 128 x 64 A tile and its HALF of the
+//              BN x 64 W tile per k-block, credited to the leader CTA's "full" barrier
+//   warp 1   : TMEM allocator; in the leader CTA also the tcgen05.mma issuer (one lane) - accumulators are
+//              double buffered in TMEM (each CTA holds its 128 rows), commits are multicast to both CTAs
+//   warps 2-17: epilogue, four warps per TMEM lane quarter: tcgen05.ld -> LayerNorm-fold / bias / activation /
+//              layer-scale / residual -> 16-bit (or fp32) rows to global, optional row re-ordering / pixel shuffle,
+//              optional per-row (sum, sum^2) statistics for the next LayerNorm-fused GEMM.
 // Replaces, on the LW-DETR path, every F.linear / nn.Conv2d / nn.ConvTranspose2d call listed in
 // SURVEY.md appendix B (reference: models/backbone/vit.py:120-140,206-220, projector.py:85-132,
 // transformer.py:27-39,466-517, ops/modules/ms_deform_attn.py:112-143, lwdetr.py:149-159).
@@ -12,6 +17,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 namespace lwb {
@@ -42,15 +48,16 @@ __device__ __forceinline__ float gelu_erf(float x) {
 struct TileCoord {
   int m_tile, n_tile, n0, cb, cy0, cx0;
 };
-__device__ __forceinline__ TileCoord decode_tile(const GemmArgs& p, int tile, int BN) {
+// pair-tile index -> this CTA's (m_tile, n_tile); n fastest, so neighbouring pairs share the A rows in L2
+__device__ __forceinline__ TileCoord decode_tile(const GemmArgs& p, int ptile, int rank, int BN) {
   TileCoord t;
-  t.n_tile = tile % p.n_tiles;      // n fastest: neighbouring CTAs share the A rows in L2
-  t.m_tile = tile / p.n_tiles;
+  t.n_tile = ptile % p.n_tiles;
+  t.m_tile = 2 * (ptile / p.n_tiles) + rank;     // may be == m_tiles for the odd tail: loads are OOB zero-fill, stores masked
   t.n0 = t.n_tile * BN;
   t.cb = t.cy0 = t.cx0 = 0;
   if (p.a_mode != AMODE_PLAIN) {
     const int per_img = p.tiles_x * p.tiles_y;
-    t.cb = t.m_tile / per_img;
+    t.cb = t.m_tile / per_img;                    // == batch for the odd tail: out of bounds in the TMA batch dimension
     const int r = t.m_tile % per_img;
     t.cy0 = (r / p.tiles_x) * p.TH;
     t.cx0 = (r % p.tiles_x) * p.TW;
@@ -58,34 +65,14 @@ __device__ __forceinline__ TileCoord decode_tile(const GemmArgs& p, int tile, in
   return t;
 }
 
-// Tile walk of a persistent CTA.  Streaming mode: tiles blockIdx.x, +gridDim.x, ... (n fastest).
-// W-stationary mode (small K): the CTA owns ONE n-tile (its W slice stays resident in shared memory) and
-// walks m-tiles  blockIdx.x / n_tiles,  + gridDim.x / n_tiles, ...  - CTAs c, c+1, .. of one m-group work on
-// the same A rows at the same time, so A is fetched from HBM once and re-read from L2.
-struct TileWalk {
-  int tile, step, end;
-  __device__ __forceinline__ TileWalk(const GemmArgs& p) {
-    if (p.w_stationary) {
-      const int groups = gridDim.x / p.n_tiles;
-      tile = (blockIdx.x / p.n_tiles) * p.n_tiles + (blockIdx.x % p.n_tiles);
-      step = groups * p.n_tiles;
-    } else {
-      tile = blockIdx.x;
-      step = gridDim.x;
-    }
-    end = p.m_tiles * p.n_tiles;
-  }
-  __device__ __forceinline__ bool valid() const { return tile < end; }
-  __device__ __forceinline__ void next() { tile += step; }
-};
-
-// Persistent: one CTA per SM walks its tiles (see TileWalk).  The smem ring (TMA -> MMA) runs
-// continuously across tiles and the accumulator is double buffered in TMEM, so the epilogue of tile i
+// Persistent CTA pairs: pair q (= blockIdx.x / 2) walks pair-tiles q, q + npairs, ...  A pair-tile is two
+// vertically adjacent 128-row m-tiles (CTA rank 0 / 1) times one BN-wide n-tile.  The smem ring (TMA -> MMA)
+// runs continuously across tiles and the accumulator is double buffered in TMEM, so the epilogue of tile i
 // overlaps the loads and MMAs of tile i+1.
 template <typename T, int BN>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmArgs p) {
-  constexpr int B_STAGE_BYTES = BN * BK * 2;
+  constexpr int B_HALF_BYTES = (BN / 2) * BK * 2;                             // this CTA's half of the W tile
   constexpr uint32_t ACC_STRIDE = BN <= 64 ? 64 : (BN <= 128 ? 128 : 256);   // TMEM columns per accumulator buffer
   constexpr uint32_t TMEM_COLS = 2 * ACC_STRIDE;
   extern __shared__ uint8_t smem_raw[];
@@ -93,88 +80,83 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int stages = p.stages;
   uint8_t* sA = smem;
   uint8_t* sB = smem + stages * A_STAGE_BYTES;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sB + p.b_slots * B_STAGE_BYTES);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sB + stages * B_HALF_BYTES);
   uint64_t* empty_bar = full_bar + MAX_STAGES;
   uint64_t* acc_full = empty_bar + MAX_STAGES;      // [2]
-  uint64_t* acc_empty = acc_full + 2;               // [2]
-  uint64_t* w_bar = acc_empty + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_bar + 1);
+  uint64_t* acc_empty = acc_full + 2;               // [2]  (used in the leader CTA)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
   float* s_vec = reinterpret_cast<float*>(full_bar + 32);   // 256 B of barriers, then 2 x {bias | gamma | colsum}[BN]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int num_tiles = p.m_tiles * p.n_tiles;
+  const uint32_t rank = cluster_ctarank();          // 0 = leader
+  const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+  const int m_pairs = (p.m_tiles + 1) >> 1;
+  const int num_ptiles = m_pairs * p.n_tiles;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     for (int s = 0; s < stages; ++s) {
-      mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
+      mbar_init(&full_bar[s], 2);                   // leader: own arrive.expect_tx + the peer's remote arrive
+      mbar_init(&empty_bar[s], 1);                  // one multicast tcgen05.commit
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&acc_full[b], 1);
-      mbar_init(&acc_empty[b], EPI_WARPS);
+      mbar_init(&acc_empty[b], 2 * EPI_WARPS);      // epilogue warps of both CTAs
     }
-    mbar_init(w_bar, 1);
     fence_mbar_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_slot, TMEM_COLS);
-    tmem_relinquish();
+    tmem_alloc2(tmem_slot, TMEM_COLS);
+    tmem_relinquish2();
   }
   tc_fence_before();
-  __syncthreads();
+  cluster_sync_all();                               // barriers of BOTH CTAs are initialised before any remote use
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
     if (lane == 0) {
-      // ------------------------------------------------------------------ TMA producer
+      // ------------------------------------------------------------------ TMA producer (both CTAs)
       uint32_t ring = 0;
-      if (p.w_stationary) {
-        // the CTA's n-tile of W (all of K) is loaded once and stays resident
-        const TileCoord tc = decode_tile(p, TileWalk(p).tile < num_tiles ? TileWalk(p).tile : 0, BN);
-        mbar_arrive_expect_tx(w_bar, static_cast<uint32_t>(p.kblocks) * B_STAGE_BYTES);
-        for (int kb = 0; kb < p.kblocks; ++kb) tma_load_2d(sB + kb * B_STAGE_BYTES, &tmB, w_bar, kb * BK, tc.n0);
-      }
-      for (TileWalk tw(p); tw.valid(); tw.next()) {
-        const TileCoord tc = decode_tile(p, tw.tile, BN);
+      for (int pt = pair; pt < num_ptiles; pt += npairs) {
+        const TileCoord tc = decode_tile(p, pt, static_cast<int>(rank), BN);
         for (int kb = 0; kb < p.kblocks; ++kb, ++ring) {
           const int s = ring % stages;
           const uint32_t ph = (ring / stages) & 1;
           mbar_wait(&empty_bar[s], ph ^ 1);
-          mbar_arrive_expect_tx(&full_bar[s], p.a_stage_tx + (p.w_stationary ? 0u : static_cast<uint32_t>(B_STAGE_BYTES)));
           uint8_t* a_dst = sA + s * A_STAGE_BYTES;
           if (p.a_mode == AMODE_PLAIN) {
-            tma_load_2d(a_dst, &tmA, &full_bar[s], kb * BK, tc.m_tile * BM);
+            tma2_load_2d(a_dst, &tmA, &full_bar[s], kb * BK, tc.m_tile * BM);
           } else {
             const int tap = kb / p.cin_blocks;
             const int c0 = (kb % p.cin_blocks) * BK;
             const int dy = tap / 3, dx = tap % 3;
             if (p.a_mode == AMODE_CONV3_S1) {
-              tma_load_4d(a_dst, &tmA, &full_bar[s], c0, tc.cx0 + dx - 1, tc.cy0 + dy - 1, tc.cb);
+              tma2_load_4d(a_dst, &tmA, &full_bar[s], c0, tc.cx0 + dx - 1, tc.cy0 + dy - 1, tc.cb);
             } else {
               // input row iy = 2*oy + dy - 1 = 2*(oy + yoff) + py ; same for columns
               const int py = (dy == 1) ? 0 : 1, yoff = (dy == 0) ? -1 : 0;
               const int px = (dx == 1) ? 0 : 1, xoff = (dx == 0) ? -1 : 0;
-              tma_load_5d(a_dst, &tmA, &full_bar[s], px * p.lda + c0, tc.cx0 + xoff, py, tc.cy0 + yoff, tc.cb);
+              tma2_load_5d(a_dst, &tmA, &full_bar[s], px * p.lda + c0, tc.cx0 + xoff, py, tc.cy0 + yoff, tc.cb);
             }
           }
-          if (!p.w_stationary) tma_load_2d(sB + s * B_STAGE_BYTES, &tmB, &full_bar[s], kb * BK, tc.n0);
+          tma2_load_2d(sB + s * B_HALF_BYTES, &tmB, &full_bar[s], kb * BK, tc.n0 + static_cast<int>(rank) * (BN / 2));
+          if (rank == 0) mbar_arrive_expect_tx(&full_bar[s], 2u * (p.a_stage_tx + B_HALF_BYTES));
+          else mbar_arrive_cluster(&full_bar[s], 0);
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ------------------------------------------------------------------ MMA issuer
-      constexpr uint32_t idesc = umma_idesc_f16(Cvt<T>::is_bf16, BM, BN);
+    if (lane == 0 && rank == 0) {
+      // ------------------------------------------------------------------ MMA issuer (leader CTA only)
+      constexpr uint32_t idesc = umma_idesc_f16(Cvt<T>::is_bf16, 2 * BM, BN);
       uint32_t ring = 0;
       int it = 0;
-      if (p.w_stationary) mbar_wait(w_bar, 0);
-      for (TileWalk tw(p); tw.valid(); tw.next(), ++it) {
+      for (int pt = pair; pt < num_ptiles; pt += npairs, ++it) {
         const int buf = it & 1;
-        mbar_wait(&acc_empty[buf], ((it >> 1) & 1) ^ 1);     // epilogue has drained this accumulator buffer
+        mbar_wait(&acc_empty[buf], ((it >> 1) & 1) ^ 1);     // both epilogues have drained this accumulator buffer
         tc_fence_after();
         const uint32_t tacc = tmem_base + buf * ACC_STRIDE;
         for (int kb = 0; kb < p.kblocks; ++kb, ++ring) {
@@ -183,28 +165,28 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           mbar_wait(&full_bar[s], ph);
           tc_fence_after();
           const uint64_t adesc = umma_desc_k128(smem_u32(sA + s * A_STAGE_BYTES));
-          const uint64_t bdesc = umma_desc_k128(smem_u32(sB + (p.w_stationary ? kb : s) * B_STAGE_BYTES));
+          const uint64_t bdesc = umma_desc_k128(smem_u32(sB + s * B_HALF_BYTES));
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
             // advance 16 elements (32 B) along K inside the 128 B swizzle row: +2 in 16-byte units
-            umma_f16_ss(tacc, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            umma2_f16_ss(tacc, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
           }
-          umma_commit(&empty_bar[s]);
+          umma2_commit_both(&empty_bar[s]);                   // frees the stage in both CTAs
         }
-        umma_commit(&acc_full[buf]);
+        umma2_commit_both(&acc_full[buf]);
       }
     }
   } else {
-    // -------------------------------------------------------------------- epilogue (8 warps)
+    // -------------------------------------------------------------------- epilogue (16 warps, both CTAs)
     const int quarter = warp & 3;               // TMEM lanes [32*quarter, 32*quarter+32) (hardware: warp_id % 4)
     const int chalf = (warp - 2) >> 2;          // which slice of the tile's 16-column chunks this warp owns
-    const int r = quarter * 32 + lane;          // row inside the tile
+    const int r = quarter * 32 + lane;          // row inside this CTA's 128-row tile
     const bool has_gamma = p.gamma != nullptr;
     const bool ln_in = p.stats_in != nullptr;
     const int act = p.act;
     int it = 0;
-    for (TileWalk tw(p); tw.valid(); tw.next(), ++it) {
-      const TileCoord tc = decode_tile(p, tw.tile, BN);
+    for (int pt = pair; pt < num_ptiles; pt += npairs, ++it) {
+      const TileCoord tc = decode_tile(p, pt, static_cast<int>(rank), BN);
       const int n0 = tc.n0;
       const int buf = it & 1;
       int m, b = 0, y = 0, x = 0;
@@ -231,7 +213,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         y = tc.cy0 + ry;
         x = tc.cx0 + (r - ry * p.TW);
         b = tc.cb;
-        valid = (r < p.TW * p.TH) && (y < p.OH) && (x < p.OW);
+        valid = (tc.m_tile < p.m_tiles) && (r < p.TW * p.TH) && (y < p.OH) && (x < p.OW);
         m = (b * p.OH + y) * p.OW + x;
       }
       long long out_row = m;
@@ -315,7 +297,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
         } else if (act == ACT_SILU) {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] = v[j] / (1.f + __expf(-v[j]));
+          for (int j = 0; j < 16; ++j) v[j] = __fdividef(v[j], 1.f + __expf(-v[j]));
         }
         if (has_gamma) {
           const float4* sg = reinterpret_cast<const float4*>(s_gamma + c * 16);
@@ -383,17 +365,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
       if (p.stats_out != nullptr && valid)
         p.stats_out[static_cast<long long>(m) * p.stats_parts_out + tc.n_tile * (EPI_WARPS / 4) + chalf] = make_float2(st_sum, st_sq);
-      // release the accumulator buffer to the MMA warp
+      // release this CTA's half of the accumulator buffer to the (leader's) MMA warp
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&acc_empty[buf]);
+      if (lane == 0) {
+        if (rank == 0) mbar_arrive(&acc_empty[buf]);
+        else mbar_arrive_cluster(&acc_empty[buf], 0);
+      }
     }
   }
 
-  __syncthreads();
+  tc_fence_before();
+  cluster_sync_all();                               // nobody frees TMEM / exits while its peer may still use it
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, TMEM_COLS);
+    tmem_dealloc2(tmem_base, TMEM_COLS);
   }
 }
 
@@ -426,8 +412,8 @@ static int pick_bn(int N, int m_tiles) {
     bn = best;
   }
   // Small problems: prefer more CTAs over wider tiles so that all 148 SMs get work.
-  auto tiles = [&](int b) { return static_cast<long long>(m_tiles) * ((N + b - 1) / b); };
-  while (bn > 64 && tiles(bn) < 148) {
+  auto tiles = [&](int b) { return static_cast<long long>((m_tiles + 1) / 2) * ((N + b - 1) / b); };
+  while (bn > 64 && tiles(bn) < 74) {
     const int nb = bn == 256 ? 128 : (bn == 192 ? 64 : 64);
     if (((N + nb - 1) / nb) * nb - N > ((N + bn - 1) / bn) * bn - N + 32) break;
     bn = nb;
@@ -512,32 +498,18 @@ int gemm_build(const GemmDesc& d, GemmOp* op, std::string* err) {
   {
     const cuuint64_t dims[2] = {static_cast<cuuint64_t>(d.K), static_cast<cuuint64_t>(d.N)};
     const cuuint64_t strides[1] = {static_cast<cuuint64_t>(d.K) * 2};
-    const cuuint32_t box[2] = {BK, static_cast<cuuint32_t>(bn)};
+    const cuuint32_t box[2] = {BK, static_cast<cuuint32_t>(bn / 2)};      // each CTA of a pair loads half of the n-tile
     if (encode(&op->tb, d.dtype, 2, d.W, dims, strides, box, err)) return -1;
   }
-  const int b_stage = bn * BK * 2;
-  const int budget = 200 * 1024;
-  // W-stationary when the CTA's whole W slice (all of K) fits beside a useful A ring
-  const bool wstat = d.a_mode == AMODE_PLAIN && static_cast<long long>(a.kblocks) * b_stage <= 150 * 1024 &&
-                     static_cast<long long>(m_tiles) * a.n_tiles >= 2LL * num_sms();
-  int stages;
-  if (wstat) {
-    stages = (budget - a.kblocks * b_stage) / A_STAGE_BYTES;
-    a.b_slots = a.kblocks;
-  } else {
-    stages = budget / (A_STAGE_BYTES + b_stage);
-  }
+  const int stage_bytes = A_STAGE_BYTES + (bn / 2) * BK * 2;
+  int stages = (200 * 1024) / stage_bytes;
   stages = std::min(stages, MAX_STAGES);
   stages = std::max(2, std::min(stages, std::max(2, 2 * a.kblocks)));
-  if (!wstat) a.b_slots = stages;
-  a.w_stationary = wstat ? 1 : 0;
   a.stages = stages;
   a.m_tiles = m_tiles;
-  op->smem = 1024 + static_cast<size_t>(stages) * A_STAGE_BYTES + static_cast<size_t>(a.b_slots) * b_stage + 256 + 2 * 3 * 4 * static_cast<size_t>(bn);
-  const long long tiles = static_cast<long long>(m_tiles) * a.n_tiles;
-  long long grid = std::min<long long>(tiles, num_sms());
-  if (wstat) grid = std::max<long long>(a.n_tiles, (num_sms() / a.n_tiles) * a.n_tiles);
-  op->grid = static_cast<unsigned>(grid);
+  op->smem = 1024 + static_cast<size_t>(stages) * stage_bytes + 256 + 2 * 3 * 4 * static_cast<size_t>(bn);
+  const long long ptiles = static_cast<long long>((m_tiles + 1) / 2) * a.n_tiles;
+  op->grid = 2u * static_cast<unsigned>(std::min<long long>(ptiles, num_sms() / 2));
   op->flops = 2.0 * d.M * static_cast<double>(d.N) * d.K;
   return 0;
 }

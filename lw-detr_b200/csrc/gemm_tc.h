@@ -19,8 +19,6 @@ enum : int { ROWS_PLAIN = 0, ROWS_WINDOW_MAJOR = 1 };
 struct GemmArgs {
   int M, N, kblocks;        // valid rows / valid output columns / K in units of 64
   int n_tiles, m_tiles, stages;
-  int b_slots;              // W slots in shared memory (= stages, or K/64 when W is resident)
-  int w_stationary;         // 1: the CTA keeps one n-tile of W resident and walks m-tiles
   int a_mode;
   uint32_t a_stage_tx;      // bytes TMA delivers into the A slot per stage
   // conv geometry (output grid OH x OW per image, tile TW x TH pixels, Cin/64 channel blocks)
