@@ -85,7 +85,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* acc_full = empty_bar + MAX_STAGES;      // [2]
   uint64_t* acc_empty = acc_full + 2;               // [2]  (used in the leader CTA)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
-  float* s_vec = reinterpret_cast<float*>(full_bar + 32);   // 256 B of barriers, then 2 x {bias | gamma | colsum}[BN]
+  float* s_vec = reinterpret_cast<float*>(full_bar + 32);   // 256 B of barriers, then {bias | gamma | colsum}[n_tiles * BN]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -110,6 +110,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 1) {
     tmem_alloc2(tmem_slot, TMEM_COLS);
     tmem_relinquish2();
+  }
+  // Stage the bias / layer-scale / LayerNorm column-sum vectors of ALL n-tiles once per CTA: the per-tile epilogue
+  // then has no dependent global loads except the (prefetched) residual and the per-row LayerNorm statistics.
+  {
+    const int npad = p.n_tiles * BN;
+    for (int i = threadIdx.x; i < npad; i += GEMM_THREADS) {
+      const bool in = i < p.N;
+      s_vec[i] = (p.bias != nullptr && in) ? __ldg(p.bias + i) : 0.f;
+      s_vec[npad + i] = (p.gamma != nullptr && in) ? __ldg(p.gamma + i) : 1.f;
+      s_vec[2 * npad + i] = (p.colsum != nullptr && in) ? __ldg(p.colsum + i) : 0.f;
+    }
   }
   tc_fence_before();
   cluster_sync_all();                               // barriers of BOTH CTAs are initialised before any remote use
@@ -220,18 +231,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (p.remap_rows) out_row = (static_cast<long long>(b) * p.IH + y) * p.IW + x;
       const long long res_row = p.resid_mod > 0 ? (m % p.resid_mod) : m;
 
-      // Stage this tile's bias / layer-scale / column-sum vectors in shared memory (double buffered by tile
-      // parity, one named barrier per tile): the per-chunk loop then has no dependent global loads except the
-      // (prefetched) residual.
-      float* s_bias = s_vec + buf * 3 * BN;
-      float* s_gamma = s_bias + BN;
-      float* s_csum = s_gamma + BN;
-      for (int i = threadIdx.x - 64; i < BN; i += 32 * EPI_WARPS) {
-        const bool in = (n0 + i) < p.N;
-        s_bias[i] = (p.bias != nullptr && in) ? __ldg(p.bias + n0 + i) : 0.f;
-        s_gamma[i] = (p.gamma != nullptr && in) ? __ldg(p.gamma + n0 + i) : 1.f;
-        s_csum[i] = (p.colsum != nullptr && in) ? __ldg(p.colsum + n0 + i) : 0.f;
-      }
+      const int npad = p.n_tiles * BN;
+      const float* s_bias = s_vec + n0;
+      const float* s_gamma = s_vec + npad + n0;
+      const float* s_csum = s_vec + 2 * npad + n0;
       // fused LayerNorm (consumer): combine the producer's partial sums of this row
       float ln_mean = 0.f, ln_rstd = 1.f;
       if (ln_in && valid) {
@@ -245,31 +248,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         ln_rstd = rsqrtf(fmaxf(s2 * p.ln_inv_c - ln_mean * ln_mean, 0.f) + p.ln_eps);
       }
       float st_sum = 0.f, st_sq = 0.f;
-      asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_WARPS) : "memory");
-
-      mbar_wait(&acc_full[buf], (it >> 1) & 1);
-      tc_fence_after();
-      const uint32_t taddr_row = tmem_base + buf * ACC_STRIDE + (static_cast<uint32_t>(quarter * 32) << 16);
       const T* resid_row = p.resid != nullptr ? reinterpret_cast<const T*>(p.resid) + res_row * p.ld_resid : nullptr;
 
-      constexpr int CH_PER_WARP = BN / 16 / (EPI_WARPS / 4);
-#pragma unroll 1
-      for (int c = chalf * CH_PER_WARP; c < (chalf + 1) * CH_PER_WARP; ++c) {
+      // one 16-column chunk: LN-fold / bias / activation / layer-scale / residual / store
+      auto finish_chunk = [&](int c, float (&v)[16], const U8& rr, bool rvec) {
         const int n = n0 + c * 16;
         const int nrem = p.N - n;                     // may be <= 0 for the padded tail of the last n-tile
-        const bool full = valid && nrem >= 16;
-        // residual prefetch (independent of the accumulator): issue before waiting on TMEM
-        U8 rr;
-        bool rvec = false;
-        if (full && resid_row != nullptr && (reinterpret_cast<uintptr_t>(resid_row + n) & 31) == 0) {
-          rr = ldg256(resid_row + n);
-          rvec = true;
-        }
-        float v[16];
-        __syncwarp();                                 // tcgen05.ld is .sync.aligned: reconverge first
-        tmem_ld_x16(taddr_row + c * 16, v);
-        tmem_ld_wait();
-        if (!valid || nrem <= 0) continue;
+        if (!valid || nrem <= 0) return;
+        const bool full = nrem >= 16;
         if (ln_in) {
           const float4* sc = reinterpret_cast<const float4*>(s_csum + c * 16);
 #pragma unroll
@@ -361,6 +347,48 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 st_sq = fmaf(f, f, st_sq);
               }
           }
+        }
+      };
+      // residual prefetch for a chunk (independent of the accumulator)
+      auto resid_prefetch = [&](int c, U8& rr) -> bool {
+        const int n = n0 + c * 16;
+        if (valid && (p.N - n) >= 16 && resid_row != nullptr && (reinterpret_cast<uintptr_t>(resid_row + n) & 31) == 0) {
+          rr = ldg256(resid_row + n);
+          return true;
+        }
+        return false;
+      };
+
+      constexpr int CH_PER_WARP = BN / 16 / (EPI_WARPS / 4);
+      const int c_first = chalf * CH_PER_WARP;
+      U8 rr_cur, rr_nxt;
+      bool rv_cur = resid_prefetch(c_first, rr_cur), rv_nxt = false;
+
+      mbar_wait(&acc_full[buf], (it >> 1) & 1);
+      tc_fence_after();
+      const uint32_t taddr_row = tmem_base + buf * ACC_STRIDE + (static_cast<uint32_t>(quarter * 32) << 16);
+
+      // software pipeline over this warp's chunks: the TMEM load of chunk i+1 is in flight while chunk i is finished
+      float va[16], vb[16];
+      __syncwarp();                                   // tcgen05.ld is .sync.aligned: reconverge first
+      tmem_ld_x16(taddr_row + c_first * 16, va);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < CH_PER_WARP; ++i) {
+        const int c = c_first + i;
+        float (&cur)[16] = (i & 1) ? vb : va;
+        float (&nxt)[16] = (i & 1) ? va : vb;
+        if (i + 1 < CH_PER_WARP) {
+          rv_nxt = resid_prefetch(c + 1, rr_nxt);
+          __syncwarp();
+          tmem_ld_x16(taddr_row + (c + 1) * 16, nxt);
+        }
+        finish_chunk(c, cur, rr_cur, rv_cur);
+        if (i + 1 < CH_PER_WARP) {
+          __syncwarp();
+          tmem_ld_wait();
+          rr_cur = rr_nxt;
+          rv_cur = rv_nxt;
         }
       }
       if (p.stats_out != nullptr && valid)
@@ -502,12 +530,13 @@ int gemm_build(const GemmDesc& d, GemmOp* op, std::string* err) {
     if (encode(&op->tb, d.dtype, 2, d.W, dims, strides, box, err)) return -1;
   }
   const int stage_bytes = A_STAGE_BYTES + (bn / 2) * BK * 2;
-  int stages = (200 * 1024) / stage_bytes;
+  const size_t vec_bytes = 3 * 4 * static_cast<size_t>(a.n_tiles) * bn;     // bias | gamma | colsum for all n-tiles
+  int stages = static_cast<int>((206 * 1024 - vec_bytes) / stage_bytes);
   stages = std::min(stages, MAX_STAGES);
   stages = std::max(2, std::min(stages, std::max(2, 2 * a.kblocks)));
   a.stages = stages;
   a.m_tiles = m_tiles;
-  op->smem = 1024 + static_cast<size_t>(stages) * stage_bytes + 256 + 2 * 3 * 4 * static_cast<size_t>(bn);
+  op->smem = 1024 + static_cast<size_t>(stages) * stage_bytes + 256 + vec_bytes;
   const long long ptiles = static_cast<long long>((m_tiles + 1) / 2) * a.n_tiles;
   op->grid = 2u * static_cast<unsigned>(std::min<long long>(ptiles, num_sms() / 2));
   op->flops = 2.0 * d.M * static_cast<double>(d.N) * d.K;
