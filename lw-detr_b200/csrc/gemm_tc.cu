@@ -69,7 +69,22 @@ __device__ __forceinline__ TileCoord decode_tile(const GemmArgs& p, int ptile, i
 // vertically adjacent 128-row m-tiles (CTA rank 0 / 1) times one BN-wide n-tile.  The smem ring (TMA -> MMA)
 // runs continuously across tiles and the accumulator is double buffered in TMEM, so the epilogue of tile i
 // overlaps the loads and MMAs of tile i+1.
-template <typename T, int BN>
+// EP (epilogue specialisation): EP_GENERIC keeps every feature behind runtime flags; the others compile the
+// features of the hot GEMMs in or out so the per-element instruction count stays minimal:
+//   EP_BIAS      out = acc + bias                     (16-bit out, plain rows, no LN / residual / activation)
+//   EP_BIAS_ACT  out = act(acc + bias)                (activation still a runtime switch, hoisted per chunk)
+//   EP_LN        out = LN-fold(acc) + bias            (qkv)
+//   EP_LN_GELU   out = gelu(LN-fold(acc) + bias)      (fc1)
+//   EP_RESID     out = resid + gamma*(acc + bias), optional row statistics (proj, fc2, patch embed, decoder)
+enum : int { EP_GENERIC = 0, EP_BIAS = 1, EP_BIAS_ACT = 2, EP_LN = 3, EP_LN_GELU = 4, EP_RESID = 5 };
+
+__device__ __forceinline__ float4 lds128(const float* p) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(smem_u32(p)));
+  return v;
+}
+
+template <typename T, int BN, int EP>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmArgs p) {
   constexpr int B_HALF_BYTES = (BN / 2) * BK * 2;                             // this CTA's half of the W tile
@@ -192,9 +207,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int quarter = warp & 3;               // TMEM lanes [32*quarter, 32*quarter+32) (hardware: warp_id % 4)
     const int chalf = (warp - 2) >> 2;          // which slice of the tile's 16-column chunks this warp owns
     const int r = quarter * 32 + lane;          // row inside this CTA's 128-row tile
-    const bool has_gamma = p.gamma != nullptr;
-    const bool ln_in = p.stats_in != nullptr;
-    const int act = p.act;
+    constexpr bool GEN = EP == EP_GENERIC;
+    const bool has_gamma = (GEN || EP == EP_RESID) && p.gamma != nullptr;
+    const bool ln_in = GEN ? (p.stats_in != nullptr) : (EP == EP_LN || EP == EP_LN_GELU);
+    const int act = GEN || EP == EP_BIAS_ACT ? p.act : (EP == EP_LN_GELU ? ACT_GELU : ACT_NONE);
+    const bool has_resid = (GEN || EP == EP_RESID) && p.resid != nullptr;
+    const bool do_stats = (GEN || EP == EP_RESID) && p.stats_out != nullptr;
+    const bool plain_out = !GEN;                 // 16-bit, rows in place, no pixel shuffle
     int it = 0;
     for (int pt = pair; pt < num_ptiles; pt += npairs, ++it) {
       const TileCoord tc = decode_tile(p, pt, static_cast<int>(rank), BN);
@@ -205,7 +224,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (p.a_mode == AMODE_PLAIN) {
         m = tc.m_tile * BM + r;
         valid = m < p.M;
-        if (p.remap_rows || p.shuffle_cout) {
+        if (GEN && (p.remap_rows || p.shuffle_cout)) {
           const int per = p.IH * p.IW;
           b = m / per;
           const int rem = m - b * per;
@@ -228,7 +247,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         m = (b * p.OH + y) * p.OW + x;
       }
       long long out_row = m;
-      if (p.remap_rows) out_row = (static_cast<long long>(b) * p.IH + y) * p.IW + x;
+      if (GEN && p.remap_rows) out_row = (static_cast<long long>(b) * p.IH + y) * p.IW + x;
       const long long res_row = p.resid_mod > 0 ? (m % p.resid_mod) : m;
 
       const int npad = p.n_tiles * BN;
@@ -248,7 +267,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         ln_rstd = rsqrtf(fmaxf(s2 * p.ln_inv_c - ln_mean * ln_mean, 0.f) + p.ln_eps);
       }
       float st_sum = 0.f, st_sq = 0.f;
-      const T* resid_row = p.resid != nullptr ? reinterpret_cast<const T*>(p.resid) + res_row * p.ld_resid : nullptr;
+      const T* resid_row = has_resid ? reinterpret_cast<const T*>(p.resid) + res_row * p.ld_resid : nullptr;
 
       // one 16-column chunk: LN-fold / bias / activation / layer-scale / residual / store
       auto finish_chunk = [&](int c, float (&v)[16], const U8& rr, bool rvec) {
@@ -260,7 +279,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const float4* sc = reinterpret_cast<const float4*>(s_csum + c * 16);
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            const float4 c4 = sc[j];
+            const float4 c4 = lds128(reinterpret_cast<const float*>(sc + j));
             v[4 * j] = ln_rstd * fmaf(-ln_mean, c4.x, v[4 * j]);
             v[4 * j + 1] = ln_rstd * fmaf(-ln_mean, c4.y, v[4 * j + 1]);
             v[4 * j + 2] = ln_rstd * fmaf(-ln_mean, c4.z, v[4 * j + 2]);
@@ -271,7 +290,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const float4* sb = reinterpret_cast<const float4*>(s_bias + c * 16);
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            const float4 b4 = sb[j];
+            const float4 b4 = lds128(reinterpret_cast<const float*>(sb + j));
             v[4 * j] += b4.x; v[4 * j + 1] += b4.y; v[4 * j + 2] += b4.z; v[4 * j + 3] += b4.w;
           }
         }
@@ -289,7 +308,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const float4* sg = reinterpret_cast<const float4*>(s_gamma + c * 16);
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            const float4 g4 = sg[j];
+            const float4 g4 = lds128(reinterpret_cast<const float*>(sg + j));
             v[4 * j] *= g4.x; v[4 * j + 1] *= g4.y; v[4 * j + 2] *= g4.z; v[4 * j + 3] *= g4.w;
           }
         }
@@ -300,19 +319,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             v[2 * j] += f.x;
             v[2 * j + 1] += f.y;
           }
-        } else if (resid_row != nullptr) {
+        } else if ((GEN || EP == EP_RESID) && resid_row != nullptr) {
           for (int j = 0; j < 16; ++j)
             if (j < nrem) v[j] += Cvt<T>::to_f(resid_row[n + j]);
         }
         // destination
         long long orow = out_row;
         int ocol = n;
-        if (p.shuffle_cout > 0) {
+        if (GEN && p.shuffle_cout > 0) {
           const int q = n / p.shuffle_cout;
           ocol = n - q * p.shuffle_cout;
           orow = (static_cast<long long>(b) * (2 * p.IH) + 2 * y + (q >> 1)) * (2 * p.IW) + 2 * x + (q & 1);
         }
-        if (p.out_fp32) {
+        if (!plain_out && p.out_fp32) {
           float* op = reinterpret_cast<float*>(p.out) + orow * p.ld_out + ocol;
           if (full && (reinterpret_cast<uintptr_t>(op) & 15) == 0) {
 #pragma unroll
@@ -329,7 +348,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
             for (int j = 0; j < 8; ++j) o.v[j] = Cvt<T>::pack(v[2 * j], v[2 * j + 1]);
             stg256(op, o);
-            if (p.stats_out != nullptr) {             // statistics of the ROUNDED values the consumer will read
+            if (do_stats) {                           // statistics of the ROUNDED values the consumer will read
 #pragma unroll
               for (int j = 0; j < 8; ++j) {
                 const float2 f = Cvt<T>::unpack(o.v[j]);
@@ -342,9 +361,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               if (j < nrem) {
                 const T h = Cvt<T>::from_f(v[j]);
                 op[j] = h;
-                const float f = Cvt<T>::to_f(h);
-                st_sum += f;
-                st_sq = fmaf(f, f, st_sq);
+                if (do_stats) {
+                  const float f = Cvt<T>::to_f(h);
+                  st_sum += f;
+                  st_sq = fmaf(f, f, st_sq);
+                }
               }
           }
         }
@@ -352,7 +373,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       // residual prefetch for a chunk (independent of the accumulator)
       auto resid_prefetch = [&](int c, U8& rr) -> bool {
         const int n = n0 + c * 16;
-        if (valid && (p.N - n) >= 16 && resid_row != nullptr && (reinterpret_cast<uintptr_t>(resid_row + n) & 31) == 0) {
+        if ((GEN || EP == EP_RESID) && valid && (p.N - n) >= 16 && resid_row != nullptr && (reinterpret_cast<uintptr_t>(resid_row + n) & 31) == 0) {
           rr = ldg256(resid_row + n);
           return true;
         }
@@ -391,7 +412,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           rv_cur = rv_nxt;
         }
       }
-      if (p.stats_out != nullptr && valid)
+      if (do_stats && valid)
         p.stats_out[static_cast<long long>(m) * p.stats_parts_out + tc.n_tile * (EPI_WARPS / 4) + chalf] = make_float2(st_sum, st_sq);
       // release this CTA's half of the accumulator buffer to the (leader's) MMA warp
       tc_fence_before();
@@ -543,25 +564,50 @@ int gemm_build(const GemmDesc& d, GemmOp* op, std::string* err) {
   return 0;
 }
 
-template <typename T, int BN>
+template <typename T, int BN, int EP>
 static int launch_inst(const GemmOp& op, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<T, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<T, BN, EP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
     if (e != cudaSuccess) return static_cast<int>(e);
     attr_set = true;
   }
-  gemm_tc_kernel<T, BN><<<op.grid, GEMM_THREADS, op.smem, st>>>(op.ta, op.tb, op.args);
+  gemm_tc_kernel<T, BN, EP><<<op.grid, GEMM_THREADS, op.smem, st>>>(op.ta, op.tb, op.args);
   return static_cast<int>(cudaGetLastError());
+}
+
+static int pick_ep(const GemmArgs& a) {
+  const bool special_rows = a.out_fp32 || a.remap_rows || a.shuffle_cout > 0;
+  if (special_rows) return EP_GENERIC;
+  if (a.stats_in) {
+    if (a.gamma || a.resid || a.stats_out) return EP_GENERIC;
+    if (a.act == ACT_NONE) return EP_LN;
+    if (a.act == ACT_GELU) return EP_LN_GELU;
+    return EP_GENERIC;
+  }
+  if (a.gamma || a.resid || a.stats_out) return a.act == ACT_NONE ? EP_RESID : EP_GENERIC;
+  return a.act == ACT_NONE ? EP_BIAS : EP_BIAS_ACT;
+}
+
+template <typename T, int BN>
+static int launch_ep(const GemmOp& op, cudaStream_t st) {
+  switch (pick_ep(op.args)) {
+    case EP_BIAS: return launch_inst<T, BN, EP_BIAS>(op, st);
+    case EP_BIAS_ACT: return launch_inst<T, BN, EP_BIAS_ACT>(op, st);
+    case EP_LN: return launch_inst<T, BN, EP_LN>(op, st);
+    case EP_LN_GELU: return launch_inst<T, BN, EP_LN_GELU>(op, st);
+    case EP_RESID: return launch_inst<T, BN, EP_RESID>(op, st);
+    default: return launch_inst<T, BN, EP_GENERIC>(op, st);
+  }
 }
 
 int gemm_launch(const GemmOp& op, cudaStream_t st) {
 #define LWB_BN_SWITCH(T)                                     \
   switch (op.bn) {                                           \
-    case 64: return launch_inst<T, 64>(op, st);              \
-    case 128: return launch_inst<T, 128>(op, st);            \
-    case 192: return launch_inst<T, 192>(op, st);            \
-    case 256: return launch_inst<T, 256>(op, st);            \
+    case 64: return launch_ep<T, 64>(op, st);                \
+    case 128: return launch_ep<T, 128>(op, st);              \
+    case 192: return launch_ep<T, 192>(op, st);              \
+    case 256: return launch_ep<T, 256>(op, st);              \
     default: return -1;                                      \
   }
   if (op.dtype == DT_BF16) { LWB_BN_SWITCH(__nv_bfloat16) } else { LWB_BN_SWITCH(__half) }
