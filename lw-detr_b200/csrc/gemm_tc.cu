@@ -85,7 +85,7 @@ __device__ __forceinline__ float4 lds128(const float* p) {
 }
 
 template <typename T, int BN, int EP>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
+__global__ void __cluster_dims__(2, 1, 1) __maxnreg__(112)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmArgs p) {
   constexpr int B_HALF_BYTES = (BN / 2) * BK * 2;                             // this CTA's half of the W tile
   constexpr uint32_t ACC_STRIDE = BN <= 64 ? 64 : (BN <= 128 ? 128 : 256);   // TMEM columns per accumulator buffer
@@ -389,38 +389,28 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       tc_fence_after();
       const uint32_t taddr_row = tmem_base + buf * ACC_STRIDE + (static_cast<uint32_t>(quarter * 32) << 16);
 
-      // software pipeline over this warp's chunks: the TMEM load of chunk i+1 is in flight while chunk i is finished
-      float va[16], vb[16];
+      // Pull this warp's whole accumulator slice into registers, then hand the TMEM buffer straight back to the
+      // MMA warp: the tensor core starts tile it+2 while the math / stores of tile it are still running.
+      float v[CH_PER_WARP][16];
       __syncwarp();                                   // tcgen05.ld is .sync.aligned: reconverge first
-      tmem_ld_x16(taddr_row + c_first * 16, va);
-      tmem_ld_wait();
 #pragma unroll
-      for (int i = 0; i < CH_PER_WARP; ++i) {
-        const int c = c_first + i;
-        float (&cur)[16] = (i & 1) ? vb : va;
-        float (&nxt)[16] = (i & 1) ? va : vb;
-        if (i + 1 < CH_PER_WARP) {
-          rv_nxt = resid_prefetch(c + 1, rr_nxt);
-          __syncwarp();
-          tmem_ld_x16(taddr_row + (c + 1) * 16, nxt);
-        }
-        finish_chunk(c, cur, rr_cur, rv_cur);
-        if (i + 1 < CH_PER_WARP) {
-          __syncwarp();
-          tmem_ld_wait();
-          rr_cur = rr_nxt;
-          rv_cur = rv_nxt;
-        }
-      }
-      if (do_stats && valid)
-        p.stats_out[static_cast<long long>(m) * p.stats_parts_out + tc.n_tile * (EPI_WARPS / 4) + chalf] = make_float2(st_sum, st_sq);
-      // release this CTA's half of the accumulator buffer to the (leader's) MMA warp
+      for (int i = 0; i < CH_PER_WARP; ++i) tmem_ld_x16(taddr_row + (c_first + i) * 16, v[i]);
+      tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
         if (rank == 0) mbar_arrive(&acc_empty[buf]);
         else mbar_arrive_cluster(&acc_empty[buf], 0);
       }
+#pragma unroll
+      for (int i = 0; i < CH_PER_WARP; ++i) {
+        if (i + 1 < CH_PER_WARP) rv_nxt = resid_prefetch(c_first + i + 1, rr_nxt);
+        finish_chunk(c_first + i, v[i], rr_cur, rv_cur);
+        rr_cur = rr_nxt;
+        rv_cur = rv_nxt;
+      }
+      if (do_stats && valid)
+        p.stats_out[static_cast<long long>(m) * p.stats_parts_out + tc.n_tile * (EPI_WARPS / 4) + chalf] = make_float2(st_sum, st_sq);
     }
   }
 
