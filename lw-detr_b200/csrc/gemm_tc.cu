@@ -85,7 +85,7 @@ __device__ __forceinline__ float4 lds128(const float* p) {
 }
 
 template <typename T, int BN, int EP>
-__global__ void __cluster_dims__(2, 1, 1) __maxnreg__(112)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmArgs p) {
   constexpr int B_HALF_BYTES = (BN / 2) * BK * 2;                             // this CTA's half of the W tile
   constexpr uint32_t ACC_STRIDE = BN <= 64 ? 64 : (BN <= 128 ? 128 : 256);   // TMEM columns per accumulator buffer
@@ -389,12 +389,28 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       tc_fence_after();
       const uint32_t taddr_row = tmem_base + buf * ACC_STRIDE + (static_cast<uint32_t>(quarter * 32) << 16);
 
-      // Pull this warp's whole accumulator slice into registers, then hand the TMEM buffer straight back to the
-      // MMA warp: the tensor core starts tile it+2 while the math / stores of tile it are still running.
-      float v[CH_PER_WARP][16];
+      // Pull this warp's accumulator slice into registers and hand the TMEM buffer back to the MMA warp BEFORE the
+      // math / stores: the tensor core starts tile it+2 while tile it is still being finished.  (18 warps put 5 on
+      // one scheduler, which caps the kernel at 96 registers/thread, so 4-chunk slices are pulled in two halves.)
+      constexpr int G0 = CH_PER_WARP <= 3 ? CH_PER_WARP : CH_PER_WARP / 2;     // chunks pulled before the release
+      float v[G0][16];
       __syncwarp();                                   // tcgen05.ld is .sync.aligned: reconverge first
+      if constexpr (G0 < CH_PER_WARP) {
 #pragma unroll
-      for (int i = 0; i < CH_PER_WARP; ++i) tmem_ld_x16(taddr_row + (c_first + i) * 16, v[i]);
+        for (int i = 0; i < G0; ++i) tmem_ld_x16(taddr_row + (c_first + i) * 16, v[i]);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < G0; ++i) {
+          rv_nxt = resid_prefetch(c_first + i + 1, rr_nxt);
+          finish_chunk(c_first + i, v[i], rr_cur, rv_cur);
+          rr_cur = rr_nxt;
+          rv_cur = rv_nxt;
+        }
+        __syncwarp();
+      }
+      constexpr int C1 = G0 < CH_PER_WARP ? G0 : 0;                            // first chunk of the final group
+#pragma unroll
+      for (int i = 0; i < CH_PER_WARP - C1; ++i) tmem_ld_x16(taddr_row + (c_first + C1 + i) * 16, v[i]);
       tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
@@ -403,9 +419,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         else mbar_arrive_cluster(&acc_empty[buf], 0);
       }
 #pragma unroll
-      for (int i = 0; i < CH_PER_WARP; ++i) {
-        if (i + 1 < CH_PER_WARP) rv_nxt = resid_prefetch(c_first + i + 1, rr_nxt);
-        finish_chunk(c_first + i, v[i], rr_cur, rv_cur);
+      for (int i = 0; i < CH_PER_WARP - C1; ++i) {
+        if (C1 + i + 1 < CH_PER_WARP) rv_nxt = resid_prefetch(c_first + C1 + i + 1, rr_nxt);
+        finish_chunk(c_first + C1 + i, v[i], rr_cur, rv_cur);
         rr_cur = rr_nxt;
         rv_cur = rv_nxt;
       }
