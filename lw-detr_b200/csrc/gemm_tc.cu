@@ -126,17 +126,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     tmem_alloc2(tmem_slot, TMEM_COLS);
     tmem_relinquish2();
   }
-  // Stage the bias / layer-scale / LayerNorm column-sum vectors of ALL n-tiles once per CTA: the per-tile epilogue
-  // then has no dependent global loads except the (prefetched) residual and the per-row LayerNorm statistics.
-  {
-    const int npad = p.n_tiles * BN;
-    for (int i = threadIdx.x; i < npad; i += GEMM_THREADS) {
-      const bool in = i < p.N;
-      s_vec[i] = (p.bias != nullptr && in) ? __ldg(p.bias + i) : 0.f;
-      s_vec[npad + i] = (p.gamma != nullptr && in) ? __ldg(p.gamma + i) : 1.f;
-      s_vec[2 * npad + i] = (p.colsum != nullptr && in) ? __ldg(p.colsum + i) : 0.f;
-    }
-  }
   tc_fence_before();
   cluster_sync_all();                               // barriers of BOTH CTAs are initialised before any remote use
   tc_fence_after();
@@ -214,7 +203,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const bool has_resid = (GEN || EP == EP_RESID) && p.resid != nullptr;
     const bool do_stats = (GEN || EP == EP_RESID) && p.stats_out != nullptr;
     const bool plain_out = !GEN;                 // 16-bit, rows in place, no pixel shuffle
+    // Stage the bias / layer-scale / LayerNorm column-sum vectors of ALL n-tiles once per CTA (epilogue warps only,
+    // while the producer / MMA warps already stream the first tile): the per-tile epilogue then has no dependent
+    // global loads except the (prefetched) residual and the per-row LayerNorm statistics.
+    {
+      const int npad_all = p.n_tiles * BN;
+      for (int i = threadIdx.x - 64; i < npad_all; i += 32 * EPI_WARPS) {
+        const bool in = i < p.N;
+        s_vec[i] = (p.bias != nullptr && in) ? __ldg(p.bias + i) : 0.f;
+        s_vec[npad_all + i] = (p.gamma != nullptr && in) ? __ldg(p.gamma + i) : 1.f;
+        s_vec[2 * npad_all + i] = (p.colsum != nullptr && in) ? __ldg(p.colsum + i) : 0.f;
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_WARPS) : "memory");
+    }
     int it = 0;
+    const int n_my_tiles = pair < num_ptiles ? (num_ptiles - pair + npairs - 1) / npairs : 0;
     for (int pt = pair; pt < num_ptiles; pt += npairs, ++it) {
       const TileCoord tc = decode_tile(p, pt, static_cast<int>(rank), BN);
       const int n0 = tc.n0;
@@ -414,7 +417,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) {
+      // (the release of the last two tiles is never consumed: skipping it also guarantees that no remote arrive is
+      //  still in flight when the pair leaves through the relaxed cluster rendezvous below)
+      if (lane == 0 && it + 2 < n_my_tiles) {
         if (rank == 0) mbar_arrive(&acc_empty[buf]);
         else mbar_arrive_cluster(&acc_empty[buf], 0);
       }
@@ -431,7 +436,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
 
   tc_fence_before();
-  cluster_sync_all();                               // nobody frees TMEM / exits while its peer may still use it
+  cluster_sync_relaxed();                           // nobody frees TMEM / exits while its peer may still use it
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc2(tmem_base, TMEM_COLS);

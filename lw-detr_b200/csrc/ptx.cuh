@@ -86,6 +86,12 @@ __device__ __forceinline__ uint32_t cluster_ctarank() {
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
   return r;
 }
+// execution-only rendezvous of the cluster (no memory ordering: nothing written here is read by the peer afterwards)
+__device__ __forceinline__ void cluster_sync_relaxed() {
+  __syncwarp();
+  asm volatile("barrier.cluster.arrive.relaxed;" ::: "memory");
+  asm volatile("barrier.cluster.wait;" ::: "memory");
+}
 __device__ __forceinline__ void cluster_sync_all() {
   __syncwarp();
   asm volatile("barrier.cluster.arrive.release;" ::: "memory");
