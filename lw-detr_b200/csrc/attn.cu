@@ -386,7 +386,8 @@ static int dispatch(const AttnArgs& a, int dh, cudaStream_t st) {
 
 int attention_tc_launch(int dtype, const AttnArgs& a, int dh, int C, cudaStream_t st);   // attn_tc.cu
 
-// 0 = mma.sync flash kernel everywhere, 1 = tcgen05 kernel for long packed-qkv sequences with dh >= 64 (default; measured faster there),
+// 0 = mma.sync flash kernel everywhere, 1 = tcgen05 kernel for long packed-qkv sequences with dh >= 32 (default; measured
+// 18-22 % faster there, 10 % slower at dh = 16 where the mma.sync kernel's 6 warps per scheduler hide latency better),
 // 2 = tcgen05 kernel for every long packed-qkv sequence.  Environment override for A/B measurements only.
 static int tc_policy() {
   static int v = [] {
@@ -402,7 +403,7 @@ int attention_launch(int dtype, const AttnArgs& a, int dh, cudaStream_t st) {
   const bool packed = dk > 0 && dv == 2 * dk && a.ldq == a.ldk && a.ldq == a.ldv && dk == static_cast<long long>(a.heads) * dh &&
                       a.ldq >= 3 * dk && (reinterpret_cast<uintptr_t>(a.q) & 15) == 0;
   const int pol = tc_policy();
-  if (packed && a.seqlen >= 512 && (pol == 2 || (pol == 1 && dh >= 64)))
+  if (packed && a.seqlen >= 512 && (pol == 2 || (pol == 1 && dh >= 32)))
     return attention_tc_launch(dtype, a, dh, static_cast<int>(dk), st);
   return dtype == DT_BF16 ? dispatch<__nv_bfloat16>(a, dh, st) : dispatch<__half>(a, dh, st);
 }

@@ -17,7 +17,9 @@ def _tol(dt):
 @pytest.mark.parametrize("dt", DTYPES)
 @pytest.mark.parametrize("nseq,seqlen,heads,dh", [(32, 100, 12, 16), (2, 1600, 12, 16), (16, 100, 12, 32), (1, 1600, 12, 32),
                                                   (16, 100, 12, 64), (1, 1600, 12, 64), (3, 300, 8, 32), (2, 100, 8, 32),
-                                                  (2, 300, 12, 32), (5, 37, 4, 16)])
+                                                  (2, 300, 12, 32), (5, 37, 4, 16),
+                                                  # tcgen05 path (packed qkv, seqlen >= 512, dh >= 32): ragged tails, single-tile last CTA
+                                                  (2, 700, 6, 32), (3, 640, 4, 64), (2, 520, 4, 32), (1, 1153, 4, 64)])
 def test_attention_matches_softmax_reference(dt, nseq, seqlen, heads, dh):
     from b200 import capi
     g = torch.Generator(device="cuda").manual_seed(seqlen + dh)
@@ -29,6 +31,31 @@ def test_attention_matches_softmax_reference(dt, nseq, seqlen, heads, dh):
     q, k, v = [t.float().reshape(nseq, seqlen, heads, dh).transpose(1, 2) for t in (qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:])]
     ref = ((q * scale) @ k.transpose(-2, -1)).softmax(-1) @ v
     ref = ref.transpose(1, 2).reshape(nseq * seqlen, C)
+    err = (out.float() - ref).abs().max().item()
+    assert err <= _tol(dt) * ref.abs().max().item(), err
+
+
+@pytest.mark.parametrize("dt", DTYPES)
+@pytest.mark.parametrize("dh", [32, 64])
+def test_attention_late_dominant_keys(dt, dh):
+    """Keys whose scores dwarf everything seen before arrive late in the sequence: the lazily tracked row maximum of
+    the tcgen05 kernel has to move (O rescaled in TMEM) several times, and rows must still normalise exactly."""
+    from b200 import capi
+    nseq, seqlen, heads = 2, 1600, 4
+    g = torch.Generator(device="cuda").manual_seed(dh)
+    C = heads * dh
+    qkv = torch.randn(nseq * seqlen, 3 * C, device="cuda", generator=g)
+    for start, gain in ((300, 4.0), (900, 10.0), (1500, 25.0)):
+        for s0 in range(nseq):
+            qkv[s0 * seqlen + start:s0 * seqlen + start + 7, C:2 * C] *= gain
+    qkv = qkv.to(dt)
+    out = torch.full((nseq * seqlen, C), float("nan"), device="cuda", dtype=dt)
+    scale = dh ** -0.5
+    capi.attention(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], out, nseq, seqlen, heads, dh, scale)
+    q, k, v = [t.float().reshape(nseq, seqlen, heads, dh).transpose(1, 2) for t in (qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:])]
+    ref = ((q * scale) @ k.transpose(-2, -1)).softmax(-1) @ v
+    ref = ref.transpose(1, 2).reshape(nseq * seqlen, C)
+    assert torch.isfinite(out.float()).all()
     err = (out.float() - ref).abs().max().item()
     assert err <= _tol(dt) * ref.abs().max().item(), err
 
