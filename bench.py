@@ -322,6 +322,14 @@ def main():
             ach = gby / (gms * 1e-3) / 1e9
             roof = {"kernel": name, "launches_per_step": n, "bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s",
                     "frac": ach / pk["hbm_gbs"], "traffic": None, "share_of_step": gms / tot, "peak_source": pk["source"]}
+        # DRAM traffic per launch of this kernel from a committed ncu --set full capture (profiles/kernel_traffic.json);
+        # null when no capture exists for this config / batch / dtype.  Compare with the algorithmic bytes per launch.
+        roof["algorithmic_bytes_per_launch"] = gby / n
+        try:
+            with open(os.path.join(ROOT, "profiles", "kernel_traffic.json")) as f:
+                roof["traffic"] = json.load(f).get("%s:%d:%s:%s" % (cfg_name, batch, dtype_name, name))
+        except Exception:
+            pass
         if name.endswith("attn"):
             # attention at head dim 16/32 is bound by exp (MUFU, 16 ex2/clk/SM), not by the tensor pipe: report that too
             dh = (cfg.vit_dim // cfg.vit_heads) if name in ("glb_attn", "win_attn") else (cfg.hidden_dim // cfg.sa_nheads)
