@@ -141,6 +141,7 @@ def main():
     ap.add_argument("--batch", type=int, default=0, help="images per GPU per step")
     ap.add_argument("--dtype", default=None, choices=[None, "fp16", "bf16"])
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-pdl", action="store_true", help="disable programmatic dependent launch (A/B measurements)")
     ap.add_argument("--profile-out", default=None, help="write the per-op timing table (JSON) here")
     a = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -188,6 +189,7 @@ def main():
     model.assume_frozen = True
     eng = model.engine()
     eng.set_option("cuda_graph", 0 if a.no_graph else 1)
+    eng.set_option("pdl", 0 if a.no_pdl else 1)
     # inputs: two distinct device batches (fp32, 4.9 MB/image => larger than the 126 MB L2 at batch >= 26)
     xs = [synth_images(batch, seed=100 * rank + i).to(dev) for i in range(2)]
     in_bytes = xs[0].numel() * 4
@@ -360,7 +362,7 @@ def main():
         cfgd.update({"l2": "no flush needed: inputs alternate between two fp32 batches of %.0f MB and one step streams %.1f GB of "
                            "activations and weights through the kernels (>> 126 MB L2), so nothing survives from step to step"
                            % (in_bytes / 1e6, step_bytes / 1e9),
-                     "cuda_graph": not a.no_graph, "model_gflop_per_image": FLOPS_PER_IMAGE[cfg_name] / 1e9,
+                     "cuda_graph": not a.no_graph, "pdl": not a.no_pdl, "model_gflop_per_image": FLOPS_PER_IMAGE[cfg_name] / 1e9,
                      "whole_model_tensor_frac_of_sustained": value * FLOPS_PER_IMAGE[cfg_name] / (peaks()["bf16_tflops_sustained"] * 1e12)})
         print(json.dumps({
             "metric": "images/sec (640x640)", "value": value, "unit": "images/s", "n_gpus": world, "steps": a.steps, "warmup": warmup,

@@ -131,7 +131,8 @@ LWDETR_API int lwdetr_forward(lwdetr_handle* h, const void* images, int images_f
                               float* pred_boxes, const lwdetr_aux_out* aux, const int32_t* topk_override,
                               void* stream);
 
-/* options: "cuda_graph" (0/1) */
+/* options: "cuda_graph" (0/1, default 1), "fuse_layernorm" (0/1, default 1), "pdl" (0/1, default 1: programmatic dependent
+ * launch of every kernel; process-wide) */
 LWDETR_API int lwdetr_set_option(lwdetr_handle* h, const char* name, int value);
 
 /* Debug captures (tests): after the op labelled `label` runs in the next forward, its output is copied to

@@ -10,6 +10,7 @@
 // Round-1 implementation: flash-style online softmax, mma.sync m16n8k16 (fp32 accumulate), K/V
 // chunks double-buffered through shared memory with cp.async, exp2 on pre-scaled logits.
 #include "attn.h"
+#include "launch.h"
 #include "ptx.cuh"
 
 #include <algorithm>
@@ -154,6 +155,7 @@ __device__ __forceinline__ void attn_chunk(const uint32_t (&qf)[DH / 16][4], con
 
 template <typename T, int DH, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32) attn_kernel(const AttnArgs p) {
+  pdl_sync();   // programmatic dependent launch: release the successor, wait for the predecessor (launch.h)
   constexpr int QROWS = WARPS * 16;
   constexpr int LDS = DH + 8;            // padded row (elements): 16 B pad => conflict-free ldmatrix
   constexpr int CPR = DH / 8;            // 16-byte chunks per row
@@ -250,6 +252,7 @@ __global__ void __launch_bounds__(WARPS * 32) attn_kernel(const AttnArgs p) {
 // kernel runs at the larger of its HBM time and its exp (MUFU) time.
 template <typename T, int DH>
 __global__ void __launch_bounds__(7 * 32) attn_short_kernel(const AttnArgs p) {
+  pdl_sync();   // programmatic dependent launch: release the successor, wait for the predecessor (launch.h)
   constexpr int WARPS = 7, QROWS = 112, KROWS = 128, NBUF = 3;
   constexpr int LDS = DH + 8, CPR = DH / 8;
   constexpr int BUF_ELEMS = (QROWS + 2 * KROWS) * LDS;
@@ -348,7 +351,7 @@ static int launch_short(const AttnArgs& a, cudaStream_t st) {
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const long long items = static_cast<long long>(a.nseq) * a.heads;
   const unsigned grid = static_cast<unsigned>(std::min<long long>(items, static_cast<long long>(sms) * ctas_per_sm));
-  attn_short_kernel<T, DH><<<grid, 7 * 32, smem, st>>>(a);
+  launch_k(attn_short_kernel<T, DH>, dim3(grid), dim3(7 * 32), smem, st, a);
   return static_cast<int>(cudaGetLastError());
 }
 
@@ -363,7 +366,7 @@ static int launch(const AttnArgs& a, cudaStream_t st) {
     attr = true;
   }
   dim3 grid((a.seqlen + WARPS * 16 - 1) / (WARPS * 16), a.heads, a.nseq);
-  attn_kernel<T, DH, WARPS><<<grid, WARPS * 32, smem, st>>>(a);
+  launch_k(attn_kernel<T, DH, WARPS>, dim3(grid), dim3(WARPS * 32), smem, st, a);
   return static_cast<int>(cudaGetLastError());
 }
 

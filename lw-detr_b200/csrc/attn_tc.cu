@@ -23,6 +23,7 @@
 // exponentiates S(j); the two tiles ping-pong on the tensor core through two independent issuer warps.
 // TMEM columns of tile t (base t*256): S [0,128) fp32, P [128,192) 16-bit pairs, O [192,192+dh) fp32.
 #include "attn.h"
+#include "launch.h"
 #include "ptx.cuh"
 #include "tma_util.h"
 
@@ -182,6 +183,7 @@ __global__ void __launch_bounds__(TC_THREADS2, 1) attn_tc_kernel(const __grid_co
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+  pdl_sync();   // the prologue above touched no global data; everything below reads the predecessor's output
   const int tile = warp == 1 ? 0 : (warp == TC_MMA1_WARP ? 1 : (warp - 2) / TC_SOFT_WARPS);
   const uint32_t colS = tile * 256, colP = colS + 128, colO = colS + 192;
 
@@ -413,7 +415,7 @@ static int launch_tc_m(const AttnArgs& a, int C, cudaStream_t st) {
     attr = true;
   }
   dim3 grid((a.seqlen + TC_QT * TC_BM - 1) / (TC_QT * TC_BM), a.heads, a.nseq);
-  attn_tc_kernel<T, DH, POLY_MASK><<<grid, TC_THREADS2, smem, st>>>(tm, a, C);
+  launch_k(attn_tc_kernel<T, DH, POLY_MASK>, dim3(grid), dim3(TC_THREADS2), smem, st, tm, a, C);
   return static_cast<int>(cudaGetLastError());
 }
 

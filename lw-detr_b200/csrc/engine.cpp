@@ -6,6 +6,7 @@
 //   gathers) -> 3 decoder layers (GEMMs, fused attention, fused deformable gather, LNs) -> heads.
 // Reference call stack being replaced: SURVEY.md section 3.2 (lwdetr.py:111-174 and callees).
 #include "engine.h"
+#include "launch.h"
 
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
@@ -130,6 +131,11 @@ int Engine::set_option(const char* name, int value) {
   }
   if (std::strcmp(name, "cuda_graph") == 0) {
     use_graph_ = value;
+    drop_graphs();
+    return 0;
+  }
+  if (std::strcmp(name, "pdl") == 0) {                 // programmatic dependent launch of every kernel (launch.h); process-wide
+    pdl_enabled() = value ? 1 : 0;
     drop_graphs();
     return 0;
   }

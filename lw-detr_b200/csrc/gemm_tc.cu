@@ -12,6 +12,7 @@
 // SURVEY.md appendix B (reference: models/backbone/vit.py:120-140,206-220, projector.py:85-132,
 // transformer.py:27-39,466-517, ops/modules/ms_deform_attn.py:112-143, lwdetr.py:149-159).
 #include "gemm_tc.h"
+#include "launch.h"
 #include "ptx.cuh"
 #include "tma_util.h"
 
@@ -130,6 +131,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   cluster_sync_all();                               // barriers of BOTH CTAs are initialised before any remote use
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_sync();   // the prologue above touched no global data; everything below reads the predecessor's output
 
   if (warp == 0) {
     if (lane == 0) {
@@ -583,7 +585,7 @@ static int launch_inst(const GemmOp& op, cudaStream_t st) {
     if (e != cudaSuccess) return static_cast<int>(e);
     attr_set = true;
   }
-  gemm_tc_kernel<T, BN, EP><<<op.grid, GEMM_THREADS, op.smem, st>>>(op.ta, op.tb, op.args);
+  launch_k(gemm_tc_kernel<T, BN, EP>, dim3(op.grid), dim3(GEMM_THREADS), op.smem, st, op.ta, op.tb, op.args);
   return static_cast<int>(cudaGetLastError());
 }
 

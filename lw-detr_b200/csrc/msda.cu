@@ -11,6 +11,7 @@
 // sampling_offsets / attention_weights projections directly (softmax and location math fused), so
 // the [B,nq,M,L,P,2] location tensor of the reference never exists in memory.
 #include "msda.h"
+#include "launch.h"
 #include "ptx.cuh"
 
 namespace lwb {
@@ -23,6 +24,7 @@ __device__ __forceinline__ U4 ldg_nc16(const void* p) {
 
 template <typename T, int NL, int NP>   // levels, points per head and level
 __global__ void __launch_bounds__(256, (NL * NP <= 2) ? 8 : ((NL * NP <= 4) ? 6 : 4)) msda_fwd_kernel(const MsdaArgs p) {
+  pdl_sync();   // programmatic dependent launch: release the successor, wait for the predecessor (launch.h)
   constexpr int D = 16;
   constexpr int LP = NL * NP;
   const long long gid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -109,11 +111,11 @@ template <typename T>
 static int dispatch(const MsdaArgs& a, cudaStream_t st) {
   const long long threads = static_cast<long long>(a.batch) * a.nq * a.heads * 2;
   const unsigned grid = static_cast<unsigned>((threads + 255) / 256);
-  if (a.levels == 1 && a.points == 2) msda_fwd_kernel<T, 1, 2><<<grid, 256, 0, st>>>(a);
-  else if (a.levels == 2 && a.points == 4) msda_fwd_kernel<T, 2, 4><<<grid, 256, 0, st>>>(a);
-  else if (a.levels == 1 && a.points == 4) msda_fwd_kernel<T, 1, 4><<<grid, 256, 0, st>>>(a);
-  else if (a.levels == 2 && a.points == 2) msda_fwd_kernel<T, 2, 2><<<grid, 256, 0, st>>>(a);
-  else if (a.levels == 4 && a.points == 4) msda_fwd_kernel<T, 4, 4><<<grid, 256, 0, st>>>(a);
+  if (a.levels == 1 && a.points == 2) launch_k(msda_fwd_kernel<T, 1, 2>, dim3(grid), dim3(256), 0, st, a);
+  else if (a.levels == 2 && a.points == 4) launch_k(msda_fwd_kernel<T, 2, 4>, dim3(grid), dim3(256), 0, st, a);
+  else if (a.levels == 1 && a.points == 4) launch_k(msda_fwd_kernel<T, 1, 4>, dim3(grid), dim3(256), 0, st, a);
+  else if (a.levels == 2 && a.points == 2) launch_k(msda_fwd_kernel<T, 2, 2>, dim3(grid), dim3(256), 0, st, a);
+  else if (a.levels == 4 && a.points == 4) launch_k(msda_fwd_kernel<T, 4, 4>, dim3(grid), dim3(256), 0, st, a);
   else return -2;
   return static_cast<int>(cudaGetLastError());
 }

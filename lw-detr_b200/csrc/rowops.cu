@@ -2,6 +2,7 @@
 // top-k, gathers, box re-parameterisation and the sine query embedding.  All are HBM-bound; they use
 // 16/32-byte accesses, one warp per row where a row reduction is needed, and fp32 math throughout.
 #include "rowops.h"
+#include "launch.h"
 #include "ptx.cuh"
 
 #include <math_constants.h>
@@ -16,6 +17,7 @@ namespace lwb {
 // transformer.py:116-123); optional second output y2 = y + add_src (decoder: tgt + query_pos).
 template <typename T, int CHUNKS>   // CHUNKS = ceil(C / 256): 8-element chunks per lane
 __global__ void __launch_bounds__(256) layernorm_kernel(const LayerNormArgs p) {
+  pdl_sync();   // programmatic dependent launch: release the successor, wait for the predecessor (launch.h)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long row = static_cast<long long>(blockIdx.x) * 8 + warp;
   if (row >= p.rows) return;
@@ -103,10 +105,10 @@ template <typename T>
 static int ln_dispatch(const LayerNormArgs& a, cudaStream_t st) {
   const unsigned grid = static_cast<unsigned>((a.rows + 7) / 8);
   const int chunks = (a.C + 255) / 256;
-  if (chunks == 1) layernorm_kernel<T, 1><<<grid, 256, 0, st>>>(a);
-  else if (chunks == 2) layernorm_kernel<T, 2><<<grid, 256, 0, st>>>(a);
-  else if (chunks == 3) layernorm_kernel<T, 3><<<grid, 256, 0, st>>>(a);
-  else if (chunks == 4) layernorm_kernel<T, 4><<<grid, 256, 0, st>>>(a);
+  if (chunks == 1) launch_k(layernorm_kernel<T, 1>, dim3(grid), dim3(256), 0, st, a);
+  else if (chunks == 2) launch_k(layernorm_kernel<T, 2>, dim3(grid), dim3(256), 0, st, a);
+  else if (chunks == 3) launch_k(layernorm_kernel<T, 3>, dim3(grid), dim3(256), 0, st, a);
+  else if (chunks == 4) launch_k(layernorm_kernel<T, 4>, dim3(grid), dim3(256), 0, st, a);
   else return -2;
   return static_cast<int>(cudaGetLastError());
 }
@@ -121,6 +123,7 @@ int layernorm_launch(int dtype, const LayerNormArgs& a, cudaStream_t st) {
 // becomes one tcgen05 GEMM whose output is already in the layout of vit.py:353-358.
 template <typename T, typename TIn>
 __global__ void __launch_bounds__(256) patch_gather_kernel(const TIn* __restrict__ img, T* __restrict__ A, int B, int S) {
+  pdl_sync();   // programmatic dependent launch: release the successor, wait for the predecessor (launch.h)
   const int G = S / 16, T_ = G * G;
   const long long total = static_cast<long long>(B) * T_ * 48;      // (row, c, py)
   const long long id = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -156,11 +159,11 @@ int patch_gather_launch(int dtype, const void* img, int img_is_fp32, void* A, in
   const long long total = static_cast<long long>(B) * (S / 16) * (S / 16) * 48;
   const unsigned grid = static_cast<unsigned>((total + 255) / 256);
   if (dtype == DT_BF16) {
-    if (img_is_fp32) patch_gather_kernel<__nv_bfloat16, float><<<grid, 256, 0, st>>>(static_cast<const float*>(img), static_cast<__nv_bfloat16*>(A), B, S);
-    else patch_gather_kernel<__nv_bfloat16, __nv_bfloat16><<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(img), static_cast<__nv_bfloat16*>(A), B, S);
+    if (img_is_fp32) launch_k(patch_gather_kernel<__nv_bfloat16, float>, dim3(grid), dim3(256), 0, st, static_cast<const float*>(img), static_cast<__nv_bfloat16*>(A), B, S);
+    else launch_k(patch_gather_kernel<__nv_bfloat16, __nv_bfloat16>, dim3(grid), dim3(256), 0, st, static_cast<const __nv_bfloat16*>(img), static_cast<__nv_bfloat16*>(A), B, S);
   } else {
-    if (img_is_fp32) patch_gather_kernel<__half, float><<<grid, 256, 0, st>>>(static_cast<const float*>(img), static_cast<__half*>(A), B, S);
-    else patch_gather_kernel<__half, __half><<<grid, 256, 0, st>>>(static_cast<const __half*>(img), static_cast<__half*>(A), B, S);
+    if (img_is_fp32) launch_k(patch_gather_kernel<__half, float>, dim3(grid), dim3(256), 0, st, static_cast<const float*>(img), static_cast<__half*>(A), B, S);
+    else launch_k(patch_gather_kernel<__half, __half>, dim3(grid), dim3(256), 0, st, static_cast<const __half*>(img), static_cast<__half*>(A), B, S);
   }
   return static_cast<int>(cudaGetLastError());
 }
@@ -169,6 +172,7 @@ int patch_gather_launch(int dtype, const void* img, int img_is_fp32, void* A, in
 template <typename T>
 __global__ void __launch_bounds__(256) unwindow_kernel(const T* __restrict__ src, int lds, T* __restrict__ dst, int ldd,
                                                        long long rows, int C, int G) {
+  pdl_sync();   // programmatic dependent launch: release the successor, wait for the predecessor (launch.h)
   const int cpr = C / 8;
   const long long id = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (id >= rows * cpr) return;
@@ -185,8 +189,8 @@ __global__ void __launch_bounds__(256) unwindow_kernel(const T* __restrict__ src
 int unwindow_launch(int dtype, const void* src, int lds, void* dst, int ldd, long long rows, int C, int G, cudaStream_t st) {
   const long long n = rows * (C / 8);
   const unsigned grid = static_cast<unsigned>((n + 255) / 256);
-  if (dtype == DT_BF16) unwindow_kernel<<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(src), lds, static_cast<__nv_bfloat16*>(dst), ldd, rows, C, G);
-  else unwindow_kernel<<<grid, 256, 0, st>>>(static_cast<const __half*>(src), lds, static_cast<__half*>(dst), ldd, rows, C, G);
+  if (dtype == DT_BF16) launch_k(unwindow_kernel<__nv_bfloat16>, dim3(grid), dim3(256), 0, st, static_cast<const __nv_bfloat16*>(src), lds, static_cast<__nv_bfloat16*>(dst), ldd, rows, C, G);
+  else launch_k(unwindow_kernel<__half>, dim3(grid), dim3(256), 0, st, static_cast<const __half*>(src), lds, static_cast<__half*>(dst), ldd, rows, C, G);
   return static_cast<int>(cudaGetLastError());
 }
 
@@ -194,6 +198,7 @@ int unwindow_launch(int dtype, const void* src, int lds, void* dst, int ldd, lon
 template <typename T>
 __global__ void __launch_bounds__(256) add_rows_kernel(const T* __restrict__ a, int lda, long long amod, const T* __restrict__ b,
                                                        int ldb, T* __restrict__ out, int ldo, long long rows, int C) {
+  pdl_sync();   // programmatic dependent launch: release the successor, wait for the predecessor (launch.h)
   const int cpr = C / 8;
   const long long id = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (id >= rows * cpr) return;
@@ -220,13 +225,14 @@ int add_rows_launch(int dtype, const void* a, int lda, long long amod, const voi
                     long long rows, int C, cudaStream_t st) {
   const long long n = rows * (C / 8);
   const unsigned grid = static_cast<unsigned>((n + 255) / 256);
-  if (dtype == DT_BF16) add_rows_kernel<<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(a), lda, amod, static_cast<const __nv_bfloat16*>(b), ldb, static_cast<__nv_bfloat16*>(out), ldo, rows, C);
-  else add_rows_kernel<<<grid, 256, 0, st>>>(static_cast<const __half*>(a), lda, amod, static_cast<const __half*>(b), ldb, static_cast<__half*>(out), ldo, rows, C);
+  if (dtype == DT_BF16) launch_k(add_rows_kernel<__nv_bfloat16>, dim3(grid), dim3(256), 0, st, static_cast<const __nv_bfloat16*>(a), lda, amod, static_cast<const __nv_bfloat16*>(b), ldb, static_cast<__nv_bfloat16*>(out), ldo, rows, C);
+  else launch_k(add_rows_kernel<__half>, dim3(grid), dim3(256), 0, st, static_cast<const __half*>(a), lda, amod, static_cast<const __half*>(b), ldb, static_cast<__half*>(out), ldo, rows, C);
   return static_cast<int>(cudaGetLastError());
 }
 
 // ----------------------------------------------------------------------------------- row max over classes (fp32)
 __global__ void __launch_bounds__(256) rowmax_kernel(const float* __restrict__ x, int ld, int n, float* __restrict__ out, long long rows) {
+  pdl_sync();   // programmatic dependent launch: release the successor, wait for the predecessor (launch.h)
   const long long row = static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
@@ -237,7 +243,7 @@ __global__ void __launch_bounds__(256) rowmax_kernel(const float* __restrict__ x
   if (lane == 0) out[row] = m;
 }
 int rowmax_launch(const float* x, int ld, int n, float* out, long long rows, cudaStream_t st) {
-  rowmax_kernel<<<static_cast<unsigned>((rows + 7) / 8), 256, 0, st>>>(x, ld, n, out, rows);
+  launch_k(rowmax_kernel, dim3(static_cast<unsigned>((rows + 7) / 8)), dim3(256), 0, st, x, ld, n, out, rows);
   return static_cast<int>(cudaGetLastError());
 }
 
@@ -245,6 +251,7 @@ int rowmax_launch(const float* x, int ld, int n, float* out, long long rows, cud
 // torch.topk(score, nq, dim=1) (transformer.py:246): one CTA per image, bitonic sort of (score, index)
 // in shared memory; ties broken towards the lower index.
 __global__ void __launch_bounds__(1024) topk_kernel(const float* __restrict__ score, int S, int np2, int k, int* __restrict__ idx_out) {
+  pdl_sync();   // programmatic dependent launch: release the successor, wait for the predecessor (launch.h)
   extern __shared__ uint8_t sm_topk[];
   float* key = reinterpret_cast<float*>(sm_topk);
   int* val = reinterpret_cast<int*>(key + np2);
@@ -284,7 +291,7 @@ int topk_launch(const float* score, int B, int S, int k, int* idx_out, cudaStrea
     if (e != cudaSuccess) return static_cast<int>(e);
     attr = true;
   }
-  topk_kernel<<<B, 1024, smem, st>>>(score, S, np2, k, idx_out);
+  launch_k(topk_kernel, dim3(B), dim3(1024), smem, st, score, S, np2, k, idx_out);
   return static_cast<int>(cudaGetLastError());
 }
 
@@ -294,6 +301,7 @@ template <typename T>
 __global__ void __launch_bounds__(128) gather_topk_kernel(const T* __restrict__ feat, int ldf, const float* __restrict__ logits, int ldl,
                                                           int ncls, const int* __restrict__ idx, int S, int k, int d,
                                                           T* __restrict__ sel, float* __restrict__ enc_logits) {
+  pdl_sync();   // programmatic dependent launch: release the successor, wait for the predecessor (launch.h)
   const long long bj = blockIdx.x;
   const long long b = bj / k;
   const long long src = b * S + idx[bj];
@@ -305,8 +313,8 @@ __global__ void __launch_bounds__(128) gather_topk_kernel(const T* __restrict__ 
 int gather_topk_launch(int dtype, const void* feat, int ldf, const float* logits, int ldl, int ncls, const int* idx, int B, int S,
                        int k, int d, void* sel, float* enc_logits, cudaStream_t st) {
   const unsigned grid = static_cast<unsigned>(B) * k;
-  if (dtype == DT_BF16) gather_topk_kernel<<<grid, 128, 0, st>>>(static_cast<const __nv_bfloat16*>(feat), ldf, logits, ldl, ncls, idx, S, k, d, static_cast<__nv_bfloat16*>(sel), enc_logits);
-  else gather_topk_kernel<<<grid, 128, 0, st>>>(static_cast<const __half*>(feat), ldf, logits, ldl, ncls, idx, S, k, d, static_cast<__half*>(sel), enc_logits);
+  if (dtype == DT_BF16) launch_k(gather_topk_kernel<__nv_bfloat16>, dim3(grid), dim3(128), 0, st, static_cast<const __nv_bfloat16*>(feat), ldf, logits, ldl, ncls, idx, S, k, d, static_cast<__nv_bfloat16*>(sel), enc_logits);
+  else launch_k(gather_topk_kernel<__half>, dim3(grid), dim3(128), 0, st, static_cast<const __half*>(feat), ldf, logits, ldl, ncls, idx, S, k, d, static_cast<__half*>(sel), enc_logits);
   return static_cast<int>(cudaGetLastError());
 }
 
@@ -320,6 +328,7 @@ __global__ void __launch_bounds__(256) query_init_kernel(const float* __restrict
                                                          const int* __restrict__ idx, const float* __restrict__ refpoint_embed,
                                                          int k, int d, long long rows, float* __restrict__ box_ts,
                                                          float* __restrict__ refpoint, T* __restrict__ sine) {
+  pdl_sync();   // programmatic dependent launch: release the successor, wait for the predecessor (launch.h)
   const long long row = blockIdx.x;
   if (row >= rows) return;
   const int j = static_cast<int>(row % k);
@@ -353,14 +362,15 @@ __global__ void __launch_bounds__(256) query_init_kernel(const float* __restrict
 int query_init_launch(int dtype, const float* delta_ts, const float* proposals, const int* idx, const float* refpoint_embed, int B,
                       int k, int d, float* box_ts, float* refpoint, void* sine, cudaStream_t st) {
   const long long rows = static_cast<long long>(B) * k;
-  if (dtype == DT_BF16) query_init_kernel<<<static_cast<unsigned>(rows), 256, 0, st>>>(delta_ts, proposals, idx, refpoint_embed, k, d, rows, box_ts, refpoint, static_cast<__nv_bfloat16*>(sine));
-  else query_init_kernel<<<static_cast<unsigned>(rows), 256, 0, st>>>(delta_ts, proposals, idx, refpoint_embed, k, d, rows, box_ts, refpoint, static_cast<__half*>(sine));
+  if (dtype == DT_BF16) launch_k(query_init_kernel<__nv_bfloat16>, dim3(static_cast<unsigned>(rows)), dim3(256), 0, st, delta_ts, proposals, idx, refpoint_embed, k, d, rows, box_ts, refpoint, static_cast<__nv_bfloat16*>(sine));
+  else launch_k(query_init_kernel<__half>, dim3(static_cast<unsigned>(rows)), dim3(256), 0, st, delta_ts, proposals, idx, refpoint_embed, k, d, rows, box_ts, refpoint, static_cast<__half*>(sine));
   return static_cast<int>(cudaGetLastError());
 }
 
 // ----------------------------------------------------------------------------------- final boxes (lwdetr.py:149-155)
 __global__ void __launch_bounds__(256) final_boxes_kernel(const float* __restrict__ delta, const float* __restrict__ refpoint,
                                                           long long rows_per_layer, long long total, float* __restrict__ boxes) {
+  pdl_sync();   // programmatic dependent launch: release the successor, wait for the predecessor (launch.h)
   const long long id = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (id >= total) return;
   const long long row = id >> 2;
@@ -371,7 +381,7 @@ __global__ void __launch_bounds__(256) final_boxes_kernel(const float* __restric
 }
 int final_boxes_launch(const float* delta, const float* refpoint, long long rows_per_layer, int layers, float* boxes, cudaStream_t st) {
   const long long total = rows_per_layer * layers * 4;
-  final_boxes_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(delta, refpoint, rows_per_layer, total, boxes);
+  launch_k(final_boxes_kernel, dim3(static_cast<unsigned>((total + 255) / 256)), dim3(256), 0, st, delta, refpoint, rows_per_layer, total, boxes);
   return static_cast<int>(cudaGetLastError());
 }
 

@@ -1,5 +1,6 @@
 // cuTensorMapEncodeTiled through cudaGetDriverEntryPoint (see tma_util.h).
 #include "tma_util.h"
+#include "launch.h"
 
 #include <cuda_runtime.h>
 
@@ -8,6 +9,12 @@
 #include "gemm_tc.h"
 
 namespace lwb {
+
+int& pdl_enabled() {
+  static int v = 1;
+  return v;
+}
+
 
 typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                         const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
