@@ -7,8 +7,12 @@
 // qkv matrix with no permutation.  Q/K/V are addressed as row-major matrices with a leading
 // dimension and a per-head column offset, so the packed qkv GEMM output is consumed in place.
 //
-// Round-1 implementation: flash-style online softmax, mma.sync m16n8k16 (fp32 accumulate), K/V
-// chunks double-buffered through shared memory with cp.async, exp2 on pre-scaled logits.
+// Kernels in this file (register-resident flash attention: mma.sync m16n8k16 with fp32 accumulation, K/V chunks
+// in a 3-stage cp.async ring, exp2 against the running maximum of the raw scores):
+//   attn_kernel       - sequences longer than 112 tokens: global attention at head dim 16, decoder self-attention
+//   attn_short_kernel - the 100-token windows, persistent CTAs walking (window, head) items
+// Long packed-qkv sequences at head dim >= 32 are dispatched to the tcgen05 kernel in attn_tc.cu instead
+// (attention_launch below; measured crossover in DESIGN.md 3.1).
 #include "attn.h"
 #include "launch.h"
 #include "ptx.cuh"
