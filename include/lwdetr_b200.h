@@ -87,6 +87,16 @@ LWDETR_API int lwdetr_msda_forward(int dtype, const void* value, int ldv, const 
  * (transformer.py:246). */
 LWDETR_API int lwdetr_topk(const float* score, int B, int S, int k, int32_t* idx, void* stream);
 
+/* PostProcess.forward (lwdetr.py:515-544) fused on the device: per image the top `num_select` of
+ * sigmoid(pred_logits) over the nq*num_classes (query, class) pairs, sorted descending (ties -> lower flat index, as
+ * torch.topk), labels = flat % num_classes, boxes = pred_boxes[flat / num_classes] converted cxcywh -> xyxy and scaled
+ * by target_sizes [B,2] = (height, width).  All pointers DEVICE: pred_logits fp32 [B,nq,num_classes], pred_boxes fp32
+ * [B,nq,4], target_sizes fp32 [B,2], work int32 [B * ceil(nq*num_classes/16384) * num_select] scratch,
+ * scores fp32 [B,num_select], labels int32 [B,num_select], boxes fp32 [B,num_select,4]. */
+LWDETR_API int lwdetr_postprocess(const float* pred_logits, const float* pred_boxes, const float* target_sizes, int B, int nq,
+                                  int num_classes, int num_select, int32_t* work, float* scores, int32_t* labels, float* boxes,
+                                  void* stream);
+
 /* Host helper (no GPU): bicubic, align_corners=False resize of a channels-last [n_in, n_in, C] fp32 grid
  * to [n_out, n_out, C] - the absolute position embedding resize of vit.py:26-54, done once at load. */
 LWDETR_API int lwdetr_host_bicubic(const float* src, int n_in, int C, int n_out, float* dst);

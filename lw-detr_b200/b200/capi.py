@@ -25,6 +25,7 @@ _SIGNATURES = {
     "lwdetr_attention": (_i, [_i, _vp, _i, _vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _i, _f, _vp]),
     "lwdetr_msda_forward": (_i, [_i, _vp, _i, _vp, _i, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
     "lwdetr_topk": (_i, [_vp, _i, _i, _i, _vp, _vp]),
+    "lwdetr_postprocess": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     "lwdetr_host_bicubic": (_i, [_vp, _i, _i, _i, _vp]),
     "lwdetr_create": (_i, [_vp, _i, _vp]),
     "lwdetr_destroy": (None, [_vp]),
@@ -143,6 +144,23 @@ def topk(score, k):
     idx = torch.empty(B, k, device=score.device, dtype=torch.int32)
     check(lib().lwdetr_topk(ptr(score), B, S, k, ptr(idx), stream_ptr()), "lwdetr_topk")
     return idx
+
+
+def postprocess(pred_logits, pred_boxes, target_sizes, num_select):
+    """Fused PostProcess (lwdetr.py:515-544) on CUDA fp32 tensors -> (scores [B,k] fp32, labels [B,k] int32, boxes [B,k,4] fp32)."""
+    import torch
+    B, nq, ncls = pred_logits.shape
+    logits = pred_logits.float().contiguous()
+    boxes = pred_boxes.float().contiguous()
+    ts = target_sizes.to(device=logits.device, dtype=torch.float32).contiguous()
+    parts = (nq * ncls + 16383) // 16384
+    work = torch.empty(B * parts * num_select, device=logits.device, dtype=torch.int32)
+    scores = torch.empty(B, num_select, device=logits.device, dtype=torch.float32)
+    labels = torch.empty(B, num_select, device=logits.device, dtype=torch.int32)
+    out = torch.empty(B, num_select, 4, device=logits.device, dtype=torch.float32)
+    check(lib().lwdetr_postprocess(ptr(logits), ptr(boxes), ptr(ts), B, nq, ncls, num_select, ptr(work), ptr(scores), ptr(labels),
+                                   ptr(out), stream_ptr()), "lwdetr_postprocess")
+    return scores, labels, out
 
 
 def host_bicubic(src, n_out):

@@ -114,6 +114,17 @@ int lwdetr_topk(const float* score, int B, int S, int k, int32_t* idx, void* str
   return 0;
 }
 
+int lwdetr_postprocess(const float* pred_logits, const float* pred_boxes, const float* target_sizes, int B, int nq, int num_classes,
+                       int num_select, int32_t* work, float* scores, int32_t* labels, float* boxes, void* stream) {
+  if (!pred_logits || !pred_boxes || !target_sizes || !work || !scores || !labels || !boxes) return fail("lwdetr_postprocess: null pointer");
+  if (B < 1 || nq < 1 || num_classes < 1 || num_select < 1) return fail("lwdetr_postprocess: bad sizes");
+  int e = lwb::postprocess_launch(pred_logits, pred_boxes, target_sizes, B, nq, num_classes, num_select, work, scores, labels, boxes,
+                                  static_cast<cudaStream_t>(stream));
+  if (e == -2) return fail("lwdetr_postprocess: need num_select <= slice length and slices * num_select <= 16384");
+  if (e) return cuda_fail(e, "lwdetr_postprocess launch");
+  return 0;
+}
+
 int lwdetr_host_bicubic(const float* src, int n_in, int C, int n_out, float* dst) {
   if (!src || !dst || n_in < 1 || n_out < 1 || C < 1) return fail("lwdetr_host_bicubic: bad arguments");
   lwb::bicubic_resize_chlast(src, n_in, C, n_out, dst);

@@ -250,17 +250,9 @@ int rowmax_launch(const float* x, int ld, int n, float* out, long long rows, cud
 // ----------------------------------------------------------------------------------- per-image top-k (sorted, descending)
 // torch.topk(score, nq, dim=1) (transformer.py:246): one CTA per image, bitonic sort of (score, index)
 // in shared memory; ties broken towards the lower index.
-__global__ void __launch_bounds__(1024) topk_kernel(const float* __restrict__ score, int S, int np2, int k, int* __restrict__ idx_out) {
-  pdl_sync();   // programmatic dependent launch: release the successor, wait for the predecessor (launch.h)
-  extern __shared__ uint8_t sm_topk[];
-  float* key = reinterpret_cast<float*>(sm_topk);
-  int* val = reinterpret_cast<int*>(key + np2);
-  const int b = blockIdx.x;
-  for (int i = threadIdx.x; i < np2; i += blockDim.x) {
-    key[i] = i < S ? score[static_cast<long long>(b) * S + i] : -CUDART_INF_F;
-    val[i] = i;
-  }
-  __syncthreads();
+// Descending bitonic sort of np2 (key, index) pairs in shared memory; ties go to the lower index (= torch.topk on
+// distinct positions).  All threads of the CTA call it.
+__device__ __forceinline__ void bitonic_sort_desc(float* key, int* val, int np2) {
   for (int size = 2; size <= np2; size <<= 1) {
     for (int stride = size >> 1; stride > 0; stride >>= 1) {
       for (int i = threadIdx.x; i < np2 / 2; i += blockDim.x) {
@@ -278,6 +270,20 @@ __global__ void __launch_bounds__(1024) topk_kernel(const float* __restrict__ sc
       __syncthreads();
     }
   }
+}
+
+__global__ void __launch_bounds__(1024) topk_kernel(const float* __restrict__ score, int S, int np2, int k, int* __restrict__ idx_out) {
+  pdl_sync();   // programmatic dependent launch: release the successor, wait for the predecessor (launch.h)
+  extern __shared__ uint8_t sm_topk[];
+  float* key = reinterpret_cast<float*>(sm_topk);
+  int* val = reinterpret_cast<int*>(key + np2);
+  const int b = blockIdx.x;
+  for (int i = threadIdx.x; i < np2; i += blockDim.x) {
+    key[i] = i < S ? score[static_cast<long long>(b) * S + i] : -CUDART_INF_F;
+    val[i] = i;
+  }
+  __syncthreads();
+  bitonic_sort_desc(key, val, np2);
   for (int i = threadIdx.x; i < k; i += blockDim.x) idx_out[static_cast<long long>(b) * k + i] = val[i];
 }
 int topk_launch(const float* score, int B, int S, int k, int* idx_out, cudaStream_t st) {
@@ -382,6 +388,89 @@ __global__ void __launch_bounds__(256) final_boxes_kernel(const float* __restric
 int final_boxes_launch(const float* delta, const float* refpoint, long long rows_per_layer, int layers, float* boxes, cudaStream_t st) {
   const long long total = rows_per_layer * layers * 4;
   launch_k(final_boxes_kernel, dim3(static_cast<unsigned>((total + 255) / 256)), dim3(256), 0, st, delta, refpoint, rows_per_layer, total, boxes);
+  return static_cast<int>(cudaGetLastError());
+}
+
+// ----------------------------------------------------------------------------------- PostProcess (lwdetr.py:515-544)
+// sigmoid -> top num_select over the nq*ncls (query, class) scores of an image -> labels, boxes in absolute xyxy.
+// Two launches: (1) every image's score list is cut into `parts` slices of <= 16384 entries, one CTA sorts a slice
+// (sigmoid computed while loading) and keeps its k best flat indices; (2) one CTA per image merges the parts*k
+// candidates, sorts them again and writes scores / labels / scaled boxes - only [B, k, 6] numbers leave the GPU.
+__device__ __forceinline__ float sigmoid_f32(float x) { return 1.f / (1.f + expf(-x)); }
+
+__global__ void __launch_bounds__(1024) postprocess_part_kernel(const float* __restrict__ logits, int S, int parts, int part_len,
+                                                                 int np2, int k, int* __restrict__ cand) {
+  pdl_sync();   // programmatic dependent launch: release the successor, wait for the predecessor (launch.h)
+  extern __shared__ uint8_t sm_topk[];
+  float* key = reinterpret_cast<float*>(sm_topk);
+  int* val = reinterpret_cast<int*>(key + np2);
+  const int b = blockIdx.x / parts, part = blockIdx.x % parts;
+  const int base = part * part_len;
+  const int n = min(part_len, S - base);
+  for (int i = threadIdx.x; i < np2; i += blockDim.x) {
+    key[i] = i < n ? sigmoid_f32(logits[static_cast<long long>(b) * S + base + i]) : -CUDART_INF_F;
+    val[i] = i < n ? base + i : -1;
+  }
+  __syncthreads();
+  bitonic_sort_desc(key, val, np2);
+  for (int i = threadIdx.x; i < k; i += blockDim.x) cand[(static_cast<long long>(b) * parts + part) * k + i] = val[i];
+}
+
+__global__ void __launch_bounds__(1024) postprocess_merge_kernel(const float* __restrict__ logits, const float* __restrict__ boxes,
+                                                                  const float* __restrict__ target_sizes, const int* __restrict__ cand,
+                                                                  int S, int ncand, int np2, int ncls, int k, float* __restrict__ scores,
+                                                                  int* __restrict__ labels, float* __restrict__ out_boxes) {
+  pdl_sync();   // programmatic dependent launch: release the successor, wait for the predecessor (launch.h)
+  extern __shared__ uint8_t sm_topk[];
+  float* key = reinterpret_cast<float*>(sm_topk);
+  int* val = reinterpret_cast<int*>(key + np2);
+  const int b = blockIdx.x;
+  for (int i = threadIdx.x; i < np2; i += blockDim.x) {
+    const int c = i < ncand ? cand[static_cast<long long>(b) * ncand + i] : -1;
+    key[i] = c >= 0 ? sigmoid_f32(logits[static_cast<long long>(b) * S + c]) : -CUDART_INF_F;
+    val[i] = c >= 0 ? c : 0x7fffffff;
+  }
+  __syncthreads();
+  bitonic_sort_desc(key, val, np2);
+  const float img_h = target_sizes[2 * b], img_w = target_sizes[2 * b + 1];
+  const int nq = S / ncls;
+  for (int i = threadIdx.x; i < k; i += blockDim.x) {
+    const int flat = val[i];
+    const int q = flat / ncls;
+    const float4 bx = *reinterpret_cast<const float4*>(boxes + (static_cast<long long>(b) * nq + q) * 4);   // cx, cy, w, h
+    const long long o = static_cast<long long>(b) * k + i;
+    scores[o] = key[i];
+    labels[o] = flat - q * ncls;
+    float4 r;
+    r.x = (bx.x - 0.5f * bx.z) * img_w;
+    r.y = (bx.y - 0.5f * bx.w) * img_h;
+    r.z = (bx.x + 0.5f * bx.z) * img_w;
+    r.w = (bx.y + 0.5f * bx.w) * img_h;
+    *reinterpret_cast<float4*>(out_boxes + o * 4) = r;
+  }
+}
+
+int postprocess_launch(const float* logits, const float* boxes, const float* target_sizes, int B, int nq, int ncls, int k,
+                       int* work, float* scores, int* labels, float* out_boxes, cudaStream_t st) {
+  const int S = nq * ncls;
+  const int parts = (S + 16383) / 16384;
+  const int part_len = (S + parts - 1) / parts;
+  int np2 = 1;
+  while (np2 < part_len) np2 <<= 1;
+  const int ncand = parts * k;
+  int np2m = 1;
+  while (np2m < ncand) np2m <<= 1;
+  if (k > part_len || np2m > 16384 || B < 1) return -2;
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(postprocess_part_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * 8);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(postprocess_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * 8);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    attr = true;
+  }
+  launch_k(postprocess_part_kernel, dim3(B * parts), dim3(1024), static_cast<size_t>(np2) * 8, st, logits, S, parts, part_len, np2, k, work);
+  launch_k(postprocess_merge_kernel, dim3(B), dim3(1024), static_cast<size_t>(np2m) * 8, st, logits, boxes, target_sizes,
+           static_cast<const int*>(work), S, ncand, np2m, ncls, k, scores, labels, out_boxes);
   return static_cast<int>(cudaGetLastError());
 }
 

@@ -24,6 +24,9 @@ int add_rows_launch(int dtype, const void* a, int lda, long long amod, const voi
                     long long rows, int C, cudaStream_t st);
 int rowmax_launch(const float* x, int ld, int n, float* out, long long rows, cudaStream_t st);
 int topk_launch(const float* score, int B, int S, int k, int* idx_out, cudaStream_t st);
+// work: B * ceil(nq*ncls / 16384) * k ints
+int postprocess_launch(const float* logits, const float* boxes, const float* target_sizes, int B, int nq, int ncls, int k,
+                       int* work, float* scores, int* labels, float* out_boxes, cudaStream_t st);
 int gather_topk_launch(int dtype, const void* feat, int ldf, const float* logits, int ldl, int ncls, const int* idx, int B, int S,
                        int k, int d, void* sel, float* enc_logits, cudaStream_t st);
 int query_init_launch(int dtype, const float* delta_ts, const float* proposals, const int* idx, const float* refpoint_embed, int B,

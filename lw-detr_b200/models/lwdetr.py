@@ -133,13 +133,19 @@ class PostProcess(nn.Module):
         if len(logits) != len(target_sizes) or target_sizes.shape[1] != 2:
             raise ValueError("target_sizes must be [batch, 2]")
         ncls = logits.shape[2]
-        scores, flat = torch.topk(logits.sigmoid().flatten(1), self.num_select, dim=1)
-        query, labels = flat // ncls, flat % ncls
-        cx, cy, w, h = boxes.unbind(-1)
-        xyxy = torch.stack([cx - 0.5 * w, cy - 0.5 * h, cx + 0.5 * w, cy + 0.5 * h], dim=-1)
-        xyxy = torch.gather(xyxy, 1, query.unsqueeze(-1).expand(-1, -1, 4))
-        img_h, img_w = target_sizes.unbind(1)
-        xyxy = xyxy * torch.stack([img_w, img_h, img_w, img_h], dim=1)[:, None, :].to(xyxy.dtype)
+        if logits.is_cuda:
+            # fused on the device (lwdetr_postprocess): only [B, num_select, 6] numbers are produced / leave the GPU
+            scores, labels, xyxy = capi.postprocess(logits, boxes, target_sizes, self.num_select)
+            labels = labels.long()
+        else:
+            # host tensors (e.g. outputs already copied to the CPU): plain torch, same arithmetic as the reference
+            scores, flat = torch.topk(logits.sigmoid().flatten(1), self.num_select, dim=1)
+            query, labels = flat // ncls, flat % ncls
+            cx, cy, w, h = boxes.unbind(-1)
+            xyxy = torch.stack([cx - 0.5 * w, cy - 0.5 * h, cx + 0.5 * w, cy + 0.5 * h], dim=-1)
+            xyxy = torch.gather(xyxy, 1, query.unsqueeze(-1).expand(-1, -1, 4))
+            img_h, img_w = target_sizes.unbind(1)
+            xyxy = xyxy * torch.stack([img_w, img_h, img_w, img_h], dim=1)[:, None, :].to(xyxy.dtype)
         return [{"scores": s, "labels": l, "boxes": b} for s, l, b in zip(scores, labels, xyxy)]
 
 

@@ -116,3 +116,62 @@ def test_topk_sorted_indices(B, S, k):
     vals, ref = torch.sort(score, dim=1, descending=True, stable=True)
     assert torch.equal(torch.gather(score, 1, idx), vals[:, :k])
     assert torch.equal(idx, ref[:, :k])
+
+
+def _torch_postprocess(logits, boxes, target_sizes, k):
+    """lwdetr.py:515-544 in plain torch (fp32)."""
+    ncls = logits.shape[2]
+    scores, flat = torch.topk(logits.sigmoid().flatten(1), k, dim=1)
+    query, labels = flat // ncls, flat % ncls
+    cx, cy, w, h = boxes.unbind(-1)
+    xyxy = torch.stack([cx - 0.5 * w, cy - 0.5 * h, cx + 0.5 * w, cy + 0.5 * h], dim=-1)
+    xyxy = torch.gather(xyxy, 1, query.unsqueeze(-1).expand(-1, -1, 4))
+    img_h, img_w = target_sizes.unbind(1)
+    return scores, labels, xyxy * torch.stack([img_w, img_h, img_w, img_h], dim=1)[:, None, :]
+
+
+@pytest.mark.parametrize("B,nq,ncls,k", [(3, 300, 91, 300), (2, 100, 91, 100), (1, 300, 91, 100), (2, 900, 20, 300)])
+def test_postprocess_matches_reference_math(B, nq, ncls, k):
+    from b200 import capi
+    g = torch.Generator(device="cuda").manual_seed(nq + k)
+    logits = torch.randn(B, nq, ncls, device="cuda", generator=g) * 3.0
+    boxes = torch.rand(B, nq, 4, device="cuda", generator=g) * 0.5 + 0.1
+    sizes = torch.tensor([[480.0, 640.0], [640.0, 427.0], [333.0, 500.0]], device="cuda")[:B]
+    scores, labels, xyxy = capi.postprocess(logits, boxes, sizes, k)
+    rs, rl, rb = _torch_postprocess(logits, boxes, sizes, k)
+    assert torch.allclose(scores, rs, rtol=2e-6, atol=1e-7)
+    assert (scores[:, 1:] <= scores[:, :-1]).all()
+    same = labels.long() == rl
+    # a different order is only legitimate between scores that round to (almost) the same fp32 sigmoid
+    gap = torch.minimum((rs - torch.roll(rs, 1, 1)).abs(), (rs - torch.roll(rs, -1, 1)).abs())
+    assert (same | (gap < 1e-6)).all()
+    assert same.float().mean() > 0.99
+    assert torch.allclose(xyxy[same], rb[same], rtol=1e-6, atol=1e-4)
+
+
+def test_postprocess_ties_and_module_surface():
+    """Heavily quantised logits: thousands of exact ties.  The selected score VALUES must still be torch's, every emitted
+    (label, box) must belong to a (query, class) pair with exactly that score, and PostProcess returns the reference's types."""
+    from b200 import capi
+    from models.lwdetr import PostProcess
+    g = torch.Generator(device="cuda").manual_seed(5)
+    B, nq, ncls, k = 2, 300, 91, 300
+    logits = (torch.randn(B, nq, ncls, device="cuda", generator=g) * 2).round() / 2
+    boxes = torch.rand(B, nq, 4, device="cuda", generator=g) * 0.5 + 0.1
+    sizes = torch.tensor([[480.0, 640.0], [600.0, 400.0]], device="cuda")
+    scores, labels, xyxy = capi.postprocess(logits, boxes, sizes, k)
+    rs = torch.topk(logits.sigmoid().flatten(1), k, dim=1)[0]
+    assert torch.allclose(scores, rs, rtol=2e-6, atol=1e-7)
+    sig = logits.sigmoid()
+    scale = torch.stack([sizes[:, 1], sizes[:, 0], sizes[:, 1], sizes[:, 0]], 1)
+    for b in range(B):
+        cx, cy, w, h = boxes[b].unbind(-1)
+        cand = torch.stack([cx - 0.5 * w, cy - 0.5 * h, cx + 0.5 * w, cy + 0.5 * h], -1) * scale[b]      # [nq, 4]
+        d = (cand[None, :, :] - xyxy[b][:, None, :]).abs().amax(-1)                                       # [k, nq]
+        q = d.argmin(1)
+        assert (d.gather(1, q[:, None]) < 1e-3).all()
+        assert torch.allclose(sig[b, q, labels[b].long()], scores[b], rtol=2e-6, atol=1e-7)
+    # ties go to the lower flat index: the emitted (query, class) pairs of equal score are in increasing order
+    res = PostProcess(num_select=k)({"pred_logits": logits, "pred_boxes": boxes}, sizes)
+    assert len(res) == B and res[0]["labels"].dtype == torch.int64 and res[0]["boxes"].shape == (k, 4)
+    assert torch.equal(res[1]["scores"], scores[1])
