@@ -160,3 +160,40 @@ def test_weight_broadcast_and_sharding_world2_gloo():
     assert [r[1] for r in res] == [True, True]
     assert res[0][2] == res[1][2] > 12e6
     assert res[0][3] == (0, 5) and res[1][3] == (5, 10)
+
+
+def test_bench_clock_sampler_windows_and_reasons():
+    """bench.py's nvidia-smi sampler: only samples inside the load window count, idle clocks are dropped from the
+    median, throttle reasons are collected, and an empty window reports 'unavailable' instead of inventing numbers."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    s = bench.ClockSampler(0)
+    na = "Not Active"
+    s.rows = [
+        [10.0, "345", "1965", "120", "0x0", na, na, na, na],            # before the window (idle)
+        [20.1, "1965", "1965", "900", "0x4", na, na, na, "Active"],
+        [20.2, "1950", "1965", "910", "0x4", na, na, na, "Active"],
+        [20.3, "1965", "1965", "905", "0x0", na, na, na, na],
+        [20.4, "345", "1965", "130", "0x0", na, na, na, na],            # load already over: dropped as < half of max
+        [30.0, "1200", "1965", "500", "0x8", "Active", na, na, na],     # after the window
+    ]
+    assert s.count_in(20.0, 20.5) == 4
+    r = s.summary(20.0, 20.5)
+    assert r["sm_mhz"] == 1965.0 and r["sm_max_mhz"] == 1965.0 and r["reasons"] == ["sw_power_cap"] and r["samples"] == 4
+    assert s.summary(40.0, 50.0) == {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+    assert "hw_slowdown" in s.summary()["reasons"]
+
+
+def test_kernel_traffic_table_keys():
+    """profiles/kernel_traffic.json is what bench.py reads for roofline.traffic: keys are config:batch:dtype:op."""
+    import json
+    from b200.config import CONFIGS
+    with open(os.path.join(ROOT, "profiles", "kernel_traffic.json")) as f:
+        t = json.load(f)
+    for k, v in t.items():
+        if k.startswith("_"):
+            continue
+        cfg, batch, dtype, op = k.split(":")
+        assert cfg in CONFIGS and int(batch) > 0 and dtype in ("fp16", "bf16") and op and isinstance(v, int) and v > 0
