@@ -175,3 +175,22 @@ def test_postprocess_ties_and_module_surface():
     res = PostProcess(num_select=k)({"pred_logits": logits, "pred_boxes": boxes}, sizes)
     assert len(res) == B and res[0]["labels"].dtype == torch.int64 and res[0]["boxes"].shape == (k, 4)
     assert torch.equal(res[1]["scores"], scores[1])
+
+
+@pytest.mark.parametrize("name", ["tiny", "small", "large"])
+def test_postprocess_matches_reference_golden(name):
+    """The fused device PostProcess against the REFERENCE's PostProcess output on the reference's golden predictions."""
+    import os
+    import numpy as np
+    from b200 import capi
+    gold = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    g, p = np.load(os.path.join(gold, "ref_%s.npz" % name)), np.load(os.path.join(gold, "ref_postprocess.npz"))
+    logits, boxes = torch.from_numpy(g["pred_logits"]).cuda(), torch.from_numpy(g["pred_boxes"]).cuda()
+    k = int(p[name + "_num_select"][0])
+    scores, labels, xyxy = capi.postprocess(logits, boxes, torch.from_numpy(p[name + "_sizes"]).cuda(), k)
+    rs, rl, rb = [torch.from_numpy(p[name + s]).cuda() for s in ("_scores", "_labels", "_boxes")]
+    assert torch.allclose(scores, rs, rtol=2e-6, atol=1e-7)
+    same = labels.long() == rl
+    gap = torch.minimum((rs - torch.roll(rs, 1, 1)).abs(), (rs - torch.roll(rs, -1, 1)).abs())
+    assert (same | (gap < 1e-6)).all() and same.float().mean() > 0.98
+    assert torch.allclose(xyxy[same], rb[same], rtol=1e-6, atol=1e-3)

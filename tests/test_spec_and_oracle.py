@@ -117,3 +117,18 @@ def test_oracle_matches_live_reference_with_forced_topk():
     out = orc.forward(sd, cfg, x)
     assert (out["pred_logits"] - ref["pred_logits"]).abs().max().item() < 1e-4
     assert (out["pred_boxes"] - ref["pred_boxes"]).abs().max().item() < 1e-5
+
+
+@pytest.mark.parametrize("name", ["tiny", "small", "medium", "large", "xlarge"])
+def test_oracle_postprocess_matches_reference_golden(name):
+    """oracle.postprocess == the reference's PostProcess.forward (lwdetr.py:515-544) run on the reference's own golden
+    predictions (tests/golden/ref_postprocess.npz, made by tools/make_goldens.py --postprocess-only)."""
+    g = np.load(os.path.join(GOLD, "ref_%s.npz" % name))
+    p = np.load(os.path.join(GOLD, "ref_postprocess.npz"))
+    out = {"pred_logits": torch.from_numpy(g["pred_logits"]), "pred_boxes": torch.from_numpy(g["pred_boxes"])}
+    res = orc.postprocess(out, torch.from_numpy(p[name + "_sizes"]), int(p[name + "_num_select"][0]))
+    assert int(p[name + "_num_select"][0]) == min(300, CONFIGS[name].num_queries)
+    for b, r in enumerate(res):
+        assert torch.equal(r["labels"], torch.from_numpy(p[name + "_labels"][b]))
+        assert torch.equal(r["scores"], torch.from_numpy(p[name + "_scores"][b]))
+        assert torch.allclose(r["boxes"], torch.from_numpy(p[name + "_boxes"][b]), rtol=0, atol=1e-4)

@@ -31,9 +31,36 @@ def sample(t, n=2048):
     return f[::step][:n].numpy().copy()
 
 
+POST_SIZES = [[480.0, 640.0], [640.0, 427.0]]     # (height, width) per image, as PostProcess takes them
+
+
+def make_postprocess_goldens():
+    """Reference PostProcess.forward (lwdetr.py:515-544) on the reference's own golden predictions: pins the oracle's
+    postprocess() and, through it, the fused device kernel.  Only needs the existing ref_<cfg>.npz fixtures."""
+    rec = {}
+    for name, B in CASES:
+        cfg = CONFIGS[name]
+        _, _, post = ref_import.build_reference(cfg)
+        gold = np.load(os.path.join(GOLD, "ref_%s.npz" % name))
+        out = {"pred_logits": torch.from_numpy(gold["pred_logits"]), "pred_boxes": torch.from_numpy(gold["pred_boxes"])}
+        sizes = torch.tensor(POST_SIZES[:B])
+        with torch.no_grad():
+            res = post["bbox"](out, sizes)
+        rec[name + "_sizes"] = sizes.numpy()
+        rec[name + "_num_select"] = np.array([post["bbox"].num_select], dtype=np.int64)
+        rec[name + "_scores"] = torch.stack([r["scores"] for r in res]).numpy()
+        rec[name + "_labels"] = torch.stack([r["labels"] for r in res]).numpy()
+        rec[name + "_boxes"] = torch.stack([r["boxes"] for r in res]).numpy()
+        print("postprocess", name, rec[name + "_scores"].shape, "num_select", post["bbox"].num_select)
+    np.savez_compressed(os.path.join(GOLD, "ref_postprocess.npz"), **rec)
+
+
 def main():
     torch.set_num_threads(os.cpu_count())
     os.makedirs(GOLD, exist_ok=True)
+    if "--postprocess-only" in sys.argv:
+        make_postprocess_goldens()
+        return
     for name, B in CASES:
         cfg = CONFIGS[name]
         model, _, _ = ref_import.build_reference(cfg)
@@ -70,6 +97,7 @@ def main():
         rec["meta"] = np.array([B, WEIGHT_SEED, IMAGE_SEED], dtype=np.int64)
         np.savez_compressed(os.path.join(GOLD, "ref_%s.npz" % name), **rec)
         print(name, "B=%d" % B, {k: v.shape for k, v in rec.items() if k.startswith("pred")})
+    make_postprocess_goldens()
 
 
 if __name__ == "__main__":
