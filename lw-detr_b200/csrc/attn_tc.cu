@@ -12,15 +12,17 @@
 //   warps 2-9   : softmax of tile 0, warps 10-17: softmax of tile 1.  TWO threads per query row (64 keys each):
 //                 four softmax warps per scheduler instead of two hide the per-warp issue latency.
 //
-// What bounds this kernel (measured, profiles/r01e_*): reading S out of TMEM runs at 64 B/clk/SM, i.e. 16 fp32
-// scores per clock - exactly the MUFU's 16 exp/clk/SM.  So every score may cross TMEM -> registers ONCE: the
-// softmax is the single-pass online form (a two-pass version that re-read S for the maxima ran at half speed,
-// independent of head dim and of how the exponentials were scheduled).  The running maximum is kept lazily
-// (FlashAttention-4): the reference maximum of a row only moves when the new chunk exceeds it by more than 2^8,
-// so O in TMEM is rescaled (by the row's own two threads, between PV(j-1) and PV(j)) only a handful of times per
-// row; P stays <= 2^8, exact in fp32 sums and safe in 16-bit P.  Each softmax thread pulls its half row of S into
-// registers and hands the S buffer straight back, so the tensor core computes S(j+1) while the group
-// exponentiates S(j); the two tiles ping-pong on the tensor core through two independent issuer warps.
+// What bounds this kernel (measured, profiles/r01e_*, r01f_ubench_tmem_rate.txt): the softmax warps' own instruction
+// stream and the MUFU (16 exp/clk/SM) - not TMEM bandwidth (440-940 B/clk/SM measured) and not the tensor core (every
+// tcgen05.mma with N <= 64 costs 45 clk: S + PV is 500-900 clk per 128x128 score tile).  A two-pass version (maxima
+// first, then exponentials) spent ~0.6 extra instructions per score plus a second chain of waits and ran 35 %
+// slower regardless of head dim, so the softmax is the single-pass online form: every score is pulled out of TMEM
+// and touched once.  The running maximum is kept lazily (FlashAttention-4): the reference maximum of a row only
+// moves when the new chunk exceeds it by more than 2^8, so O in TMEM is rescaled (by the row's own two threads,
+// between PV(j-1) and PV(j)) only a handful of times per row; P stays <= 2^8, exact in fp32 sums and safe in 16-bit
+// P.  Each softmax thread pulls its half row of S into registers and hands the S buffer straight back, so the
+// tensor core computes S(j+1) while the group exponentiates S(j); the two tiles ping-pong on the tensor core
+// through two independent issuer warps.
 // TMEM columns of tile t (base t*256): S [0,128) fp32, P [128,192) 16-bit pairs, O [192,192+dh) fp32.
 #include "attn.h"
 #include "launch.h"
