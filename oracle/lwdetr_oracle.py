@@ -151,18 +151,30 @@ def _mlp(x, sd, p, n):
     return x
 
 
-def encoder_proposals(cfg, dtype):
-    """transformer.py:71-125 gen_encoder_output_proposals with no padding and unsigmoid=False:
-    per token (cx, cy, w, h) = ((j+.5)/W, (i+.5)/H, .05*2^lvl, .05*2^lvl); invalid -> zeros."""
+def encoder_proposals(cfg, dtype, level_masks=None):
+    """transformer.py:71-125 gen_encoder_output_proposals with unsigmoid=False:
+    per token (cx, cy, w, h) = ((j+.5)/valid_W, (i+.5)/valid_H, .05*2^lvl, .05*2^lvl); padded or out-of-(0.01,0.99)
+    -> zeros.  Without masks (same-size batch) valid_W/H are the level sizes and the table is batch independent
+    ([S,4], [S,1]); with per-level padding masks [B,H,W] (True = padding) it is per image ([B,S,4], [B,S,1])."""
     props = []
     for lvl, (H, W) in enumerate(cfg.level_shapes):
         ys, xs = torch.meshgrid(torch.arange(H, dtype=torch.float32), torch.arange(W, dtype=torch.float32), indexing="ij")
-        cx = (xs + 0.5) / W
-        cy = (ys + 0.5) / H
+        if level_masks is None:
+            cx, cy = (xs + 0.5) / W, (ys + 0.5) / H
+        else:
+            m = level_masks[lvl]
+            vh = (~m[:, :, 0]).sum(1).float()[:, None, None]          # transformer.py:87-89
+            vw = (~m[:, 0, :]).sum(1).float()[:, None, None]
+            cx, cy = (xs[None] + 0.5) / vw, (ys[None] + 0.5) / vh
         wh = torch.full_like(cx, 0.05 * (2.0 ** lvl))
-        props.append(torch.stack([cx, cy, wh, wh], -1).reshape(-1, 4))
-    props = torch.cat(props, 0)
+        props.append(torch.stack([cx, cy, wh, wh], -1).flatten(-3, -2))
+    props = torch.cat(props, -2)
     valid = ((props > 0.01) & (props < 0.99)).all(-1, keepdim=True)
+    if level_masks is not None:
+        pad = torch.cat([m.flatten(1) for m in level_masks], 1)[..., None]
+        props = props.masked_fill(pad, 0.0)                             # transformer.py:117-118
+        keep = valid & ~pad                                             # memory rows zeroed: transformer.py:121-124
+        return (props * valid).to(dtype), keep
     return (props * valid).to(dtype), valid
 
 
@@ -227,37 +239,50 @@ def decoder_self_attention(tgt, query_pos, sd, p, heads):
     return F.linear(y, sd[p + ".out_proj.weight"], sd[p + ".out_proj.bias"])
 
 
-def deformable_cross_attention(query, ref, memory, sd, p, cfg):
-    """ops/modules/ms_deform_attn.py:96-144 with 4-d reference boxes (same box at every level)."""
+def deformable_cross_attention(query, ref, memory, sd, p, cfg, pad=None):
+    """ops/modules/ms_deform_attn.py:96-144 with 4-d reference boxes.  ref is [B,Q,4] (same box at every level:
+    valid_ratio 1) or [B,Q,L,4] (boxes scaled by each level's valid ratio, transformer.py:352-353); pad [B,S] marks
+    padded memory tokens whose value rows are zeroed (ms_deform_attn.py:114-115)."""
     B, Q, d = query.shape
     M, L, P = cfg.ca_nheads, cfg.n_levels, cfg.dec_n_points
-    value = F.linear(memory, sd[p + ".value_proj.weight"], sd[p + ".value_proj.bias"]).reshape(B, -1, M, d // M)
+    value = F.linear(memory, sd[p + ".value_proj.weight"], sd[p + ".value_proj.bias"])
+    if pad is not None:
+        value = value.masked_fill(pad[..., None], 0.0)
+    value = value.reshape(B, -1, M, d // M)
     off = F.linear(query, sd[p + ".sampling_offsets.weight"], sd[p + ".sampling_offsets.bias"]).reshape(B, Q, M, L, P, 2)
     aw = F.linear(query, sd[p + ".attention_weights.weight"], sd[p + ".attention_weights.bias"]).reshape(B, Q, M, L * P)
     aw = aw.softmax(-1).reshape(B, Q, M, L, P)
-    loc = ref[:, :, None, None, None, :2] + off / P * ref[:, :, None, None, None, 2:] * 0.5
+    if ref.dim() == 3:
+        ref = ref[:, :, None, :].expand(-1, -1, L, -1)
+    loc = ref[:, :, None, :, None, :2] + off / P * ref[:, :, None, :, None, 2:] * 0.5
     y = msda_core(value, cfg.level_shapes, loc, aw)
     return F.linear(y, sd[p + ".output_proj.weight"], sd[p + ".output_proj.bias"])
 
 
-def decoder_layer(tgt, query_pos, ref, memory, sd, p, cfg):
+def decoder_layer(tgt, query_pos, ref, memory, sd, p, cfg, pad=None):
     """transformer.py:466-517 forward_post (dropout 0, LN eps 1e-5)."""
     d = tgt.shape[-1]
     ln = lambda t, n: F.layer_norm(t, (d,), sd["%s.%s.weight" % (p, n)], sd["%s.%s.bias" % (p, n)], 1e-5)
     tgt = ln(tgt + decoder_self_attention(tgt, query_pos, sd, p + ".self_attn", cfg.sa_nheads), "norm1")
-    tgt = ln(tgt + deformable_cross_attention(tgt + query_pos, ref, memory, sd, p + ".cross_attn", cfg), "norm2")
+    tgt = ln(tgt + deformable_cross_attention(tgt + query_pos, ref, memory, sd, p + ".cross_attn", cfg, pad), "norm2")
     ff = F.linear(F.relu(F.linear(tgt, sd[p + ".linear1.weight"], sd[p + ".linear1.bias"])),
                   sd[p + ".linear2.weight"], sd[p + ".linear2.bias"])
     return ln(tgt + ff, "norm3")
 
 
-def transformer_and_heads(levels, sd, cfg, topk_override=None, inter=None):
+def transformer_and_heads(levels, sd, cfg, topk_override=None, inter=None, level_masks=None):
     """transformer.py:198-288 Transformer.forward (eval: group 0 only), transformer.py:328-427 decoder
-    (lite_refpoint_refine: query_pos from the initial reference once), lwdetr.py:141-173 heads."""
+    (lite_refpoint_refine: query_pos from the initial reference once), lwdetr.py:141-173 heads.
+    level_masks: per-level padding masks [B,H,W] (True = padding) of a padded / mixed-size batch, or None."""
     memory = torch.cat(levels, 1)                                    # [B, S, d]
     B, S, d = memory.shape
     nq = cfg.num_queries
-    proposals, valid = encoder_proposals(cfg, memory.dtype)
+    proposals, valid = encoder_proposals(cfg, memory.dtype, level_masks)
+    pad = vr = None
+    if level_masks is not None:
+        pad = torch.cat([m.flatten(1) for m in level_masks], 1)                                   # transformer.py:215-217
+        vr = torch.stack([torch.stack([(~m[:, 0, :]).sum(1).float() / m.shape[2],                 # transformer.py:188-196 (w, h)
+                                       (~m[:, :, 0]).sum(1).float() / m.shape[1]], -1) for m in level_masks], 1).to(memory.dtype)
     t = "transformer"
     om = F.linear(memory * valid, sd[t + ".enc_output.0.weight"], sd[t + ".enc_output.0.bias"])
     om = F.layer_norm(om, (d,), sd[t + ".enc_output_norm.0.weight"], sd[t + ".enc_output_norm.0.bias"], 1e-5)
@@ -265,16 +290,19 @@ def transformer_and_heads(levels, sd, cfg, topk_override=None, inter=None):
     score = cls_all.max(-1)[0]
     topk = torch.topk(score, nq, dim=1)[1] if topk_override is None else topk_override
     sel = torch.gather(om, 1, topk[..., None].expand(-1, -1, d))     # memory_ts / hs_enc
-    box_ts = reparam(_mlp(sel, sd, t + ".enc_out_bbox_embed.0", 3), proposals[topk])   # per-row op: same as MLP-then-gather
+    prop_sel = proposals[topk] if proposals.dim() == 2 else torch.gather(proposals, 1, topk[..., None].expand(-1, -1, 4))
+    box_ts = reparam(_mlp(sel, sd, t + ".enc_out_bbox_embed.0", 3), prop_sel)          # per-row op: same as MLP-then-gather
     refpoint = reparam(sd["refpoint_embed.weight"][:nq][None].expand(B, -1, -1), box_ts)   # transformer.py:266-276
     tgt = sd["query_feat.weight"][:nq][None].expand(B, -1, -1)
-    query_pos = _mlp(sine_embed(refpoint, d // 2), sd, t + ".decoder.ref_point_head", 2)   # valid_ratios == 1
+    # transformer.py:345-356: reference boxes are scaled by each level's valid ratio; the sine embedding uses level 0's
+    ref_in = refpoint if vr is None else refpoint[:, :, None, :] * torch.cat([vr, vr], -1)[:, None]
+    query_pos = _mlp(sine_embed(refpoint if vr is None else ref_in[:, :, 0, :], d // 2), sd, t + ".decoder.ref_point_head", 2)
     if inter is not None:
         inter.update(memory=memory, enc_score=score, topk=topk, enc_sel=sel, box_ts=box_ts, refpoint=refpoint,
                      query_pos=query_pos)
     hs = []
     for i in range(cfg.dec_layers):
-        tgt = decoder_layer(tgt, query_pos, refpoint, memory, sd, "%s.decoder.layers.%d" % (t, i), cfg)
+        tgt = decoder_layer(tgt, query_pos, ref_in, memory, sd, "%s.decoder.layers.%d" % (t, i), cfg, pad)
         hs.append(F.layer_norm(tgt, (d,), sd[t + ".decoder.norm.weight"], sd[t + ".decoder.norm.bias"], 1e-5))
         if inter is not None:
             inter["dec%d" % i] = tgt
@@ -288,8 +316,15 @@ def transformer_and_heads(levels, sd, cfg, topk_override=None, inter=None):
     return out
 
 
-def forward(sd, cfg, images, topk_override=None, inter=None, dtype=torch.float32):
-    """Full LWDETR.forward (lwdetr.py:111-174) for same-size, unpadded batches."""
+def level_padding_masks(mask, cfg):
+    """backbone.py:150-158: the image padding mask [B,H,W] (True = padding) resized to every feature level with
+    F.interpolate's default nearest mode."""
+    return [F.interpolate(mask[None].float(), size=(H, W)).to(torch.bool)[0] for (H, W) in cfg.level_shapes]
+
+
+def forward(sd, cfg, images, topk_override=None, inter=None, dtype=torch.float32, mask=None):
+    """Full LWDETR.forward (lwdetr.py:111-174).  mask: NestedTensor.mask [B,H,W] of a padded / mixed-size batch
+    (True = padding, misc.py:317-339) or None for same-size batches."""
     with torch.no_grad():
         sd = {k: (v.to(dtype) if v.is_floating_point() else v) for k, v in sd.items()}
         taps = vit_encoder(images.to(dtype), sd, cfg, inter)
@@ -299,7 +334,8 @@ def forward(sd, cfg, images, topk_override=None, inter=None, dtype=torch.float32
                 inter["tap%d" % j] = tp
             for l, lv in enumerate(levels):
                 inter["level%d" % l] = lv
-        return transformer_and_heads(levels, sd, cfg, topk_override, inter)
+        lm = level_padding_masks(mask, cfg) if mask is not None and bool(mask.any()) else None
+        return transformer_and_heads(levels, sd, cfg, topk_override, inter, lm)
 
 
 def postprocess(out, target_sizes, num_select):

@@ -55,11 +55,44 @@ def make_postprocess_goldens():
     np.savez_compressed(os.path.join(GOLD, "ref_postprocess.npz"), **rec)
 
 
+PAD_VALID = [(640, 640), (576, 480)]              # (valid height, valid width) of the two images of the padded fixture
+
+
+def padded_inputs():
+    """Two images of different size padded to 640x640 the way util/misc.py:317-339 builds a NestedTensor."""
+    x = synth_images(2, 9).clone()
+    mask = torch.zeros(2, 640, 640, dtype=torch.bool)
+    for b, (h, w) in enumerate(PAD_VALID):
+        mask[b, h:, :] = True
+        mask[b, :, w:] = True
+        x[b][:, mask[b]] = 0
+    return x, mask
+
+
+def make_padded_golden():
+    """Reference forward on a padded / mixed-size batch (masks not all False): pins the oracle's valid-ratio,
+    proposal-masking and value-masking arithmetic ahead of the device implementation."""
+    cfg = CONFIGS["tiny"]
+    model, _, _ = ref_import.build_reference(cfg)
+    model.load_state_dict(synth_state_dict(cfg, 5), strict=True)
+    x, mask = padded_inputs()
+    nested = sys.modules["_ref_util.misc"].NestedTensor(x, mask)
+    with torch.no_grad():
+        out = model(nested)
+    np.savez_compressed(os.path.join(GOLD, "ref_tiny_padded.npz"), pred_logits=out["pred_logits"].numpy(),
+                        pred_boxes=out["pred_boxes"].numpy(), enc_boxes=out["enc_outputs"]["pred_boxes"].numpy(),
+                        valid=np.array(PAD_VALID, dtype=np.int64), meta=np.array([2, 5, 9], dtype=np.int64))
+    print("padded", out["pred_logits"].shape)
+
+
 def main():
     torch.set_num_threads(os.cpu_count())
     os.makedirs(GOLD, exist_ok=True)
     if "--postprocess-only" in sys.argv:
         make_postprocess_goldens()
+        return
+    if "--padded-only" in sys.argv:
+        make_padded_golden()
         return
     for name, B in CASES:
         cfg = CONFIGS[name]
@@ -98,6 +131,7 @@ def main():
         np.savez_compressed(os.path.join(GOLD, "ref_%s.npz" % name), **rec)
         print(name, "B=%d" % B, {k: v.shape for k, v in rec.items() if k.startswith("pred")})
     make_postprocess_goldens()
+    make_padded_golden()
 
 
 if __name__ == "__main__":
