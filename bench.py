@@ -1,7 +1,7 @@
 """LW-DETR inference throughput benchmark (BASELINE.json: images/sec at 640x640, per-GPU batch, N B200s).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--config small] [--batch 32] [--dtype fp16]
-    python bench.py --impl reference ...      # the reference algorithm's CPU forward (oracle port) on host cores
+    python bench.py --impl reference ...      # the unmodified reference's CPU forward (baseline/_ref) on the host cores
     torchrun --nproc-per-node N bench.py --gpus N ...   # one process per GPU, image-sharded replicas
 
 One "step" = one forward pass of `batch` synthetic 640x640 images per GPU through the C-ABI engine
@@ -95,40 +95,73 @@ class ClockSampler(threading.Thread):
                 continue
         if not sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
-        hot = [v for v in sm if v >= 0.5 * max(sm)]
-        return {"sm_mhz": statistics.median(hot), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+        hot = [v for v in sm if v >= 0.5 * max(sm)]      # samples taken between two launches read an idle clock
+        return {"sm_mhz": statistics.median(hot), "sm_mhz_unfiltered_median": statistics.median(sm), "sm_mhz_min": min(sm),
+                "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm), "samples_kept": len(hot)}
 
 
-def cpu_reference_run(cfg_name, steps, warmup, sample_batch, dtype_name):
-    """The reference algorithm on the host cores: the oracle port (oracle/lwdetr_oracle.py), fp32, all threads."""
+def cpu_reference_run(cfg_name, steps, warmup, sample_batch, dtype_name, full_batch=0, budget_s=0.0):
+    """The reference's CPU forward on the host cores, fp32, all the threads that help.
+    kind "reference": the UNMODIFIED reference model built by its own models.build_model(args) (tools/ref_import.py;
+    /root/reference in the build container, the byte-identical copy under baseline/_ref on the GPU box, staged by
+    tools/vendor_reference.py at build() time), cross-attention through its ms_deform_attn_core_pytorch path - the path
+    the reference itself takes on the CPU.  kind "port": the oracle port (oracle/lwdetr_oracle.py), only when no
+    reference tree is available."""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
     from b200.config import CONFIGS
     from b200.synth import synth_images, synth_state_dict
-    from oracle import lwdetr_oracle as orc
     cfg = CONFIGS[cfg_name]
     sd = synth_state_dict(cfg, 1)
     x = synth_images(sample_batch, 0)
+    kind, fwd = "port", None
+    try:
+        import ref_import
+        if ref_import.available():
+            model, _, _ = ref_import.build_reference(cfg)
+            model.load_state_dict(sd, strict=True)
+
+            def fwd():
+                with torch.no_grad():
+                    return model(x)
+            kind = "reference"
+    except Exception as ex:   # a broken copy must not take the bench line down: fall back to the port and say so
+        sys.stderr.write("reference import failed (%r): timing the oracle port instead\n" % (ex,))
+        fwd = None
+    if fwd is None:
+        from oracle import lwdetr_oracle as orc
+        fwd = lambda: orc.forward(sd, cfg, x)
     # "all the host threads it can use": torch's intra-op pool does not scale to every core of a many-core host
     # on ops this small, so pick the thread count that maximises throughput (one probe forward per candidate).
     ncpu = os.cpu_count() or 1
     best_t, best = ncpu, None
     for t in sorted({c for c in (8, 16, 32, 64, ncpu) if c <= ncpu}):
         torch.set_num_threads(t)
-        orc.forward(sd, cfg, x)
+        fwd()
         t0 = time.perf_counter()
-        orc.forward(sd, cfg, x)
+        fwd()
         el = time.perf_counter() - t0
         if best is None or el < best:
             best, best_t = el, t
     torch.set_num_threads(best_t)
-    for _ in range(warmup):
-        orc.forward(sd, cfg, x)
+    # One step = `per_step` images = per_step / sample_batch chunked forwards.  With a time budget the step is the full
+    # per-GPU batch when (steps + warmup) of those fit, else the largest multiple of the chunk that does.
+    chunks = 1
+    if full_batch and budget_s > 0:
+        t_chunk = best
+        fit = int(budget_s / max(1e-9, (steps + warmup) * t_chunk))
+        chunks = max(1, min(full_batch // sample_batch, fit))
+    for _ in range(warmup * chunks):
+        fwd()
     t0 = time.perf_counter()
-    for _ in range(steps):
-        orc.forward(sd, cfg, x)
+    for _ in range(steps * chunks):
+        fwd()
     dt = time.perf_counter() - t0
-    return {"value": steps * sample_batch / dt, "unit": "images/s", "cores": torch.get_num_threads(), "kind": "port",
-            "sample": "%d forward(s) of %d synthetic 640x640 image(s), %s, fp32 torch CPU oracle port, best of thread counts up to %d" % (steps, sample_batch, cfg_name, ncpu),
-            "ms_per_step": 1e3 * dt / steps}
+    per_step = sample_batch * chunks
+    what = "unmodified reference models.build_model forward (baseline/_ref)" if kind == "reference" else "fp32 torch CPU oracle port"
+    return {"value": steps * per_step / dt, "unit": "images/s", "cores": torch.get_num_threads(), "kind": kind,
+            "sample": "%d step(s) of %d synthetic 640x640 image(s) each (%d forward(s) of %d), LW-DETR-%s, fp32, %s, best of thread counts up to %d"
+                      % (steps, per_step, chunks, sample_batch, cfg_name, what, ncpu),
+            "ms_per_step": 1e3 * dt / steps, "images_per_step": per_step}
 
 
 def main():
@@ -157,8 +190,16 @@ def main():
     if a.impl == "reference":
         if rank != 0:
             return
-        sample = 2 if cfg_name in ("tiny", "small") else 1
-        r = cpu_reference_run(cfg_name, max(1, a.steps), a.warmup, sample, dtype_name)
+        # a bounded sample of the workload: the CPU forward is per-image independent, so images/s on a batch of
+        # `sample` images is the same metric; the batch the reference arm ACTUALLY ran is what config states
+        chunk = 4 if cfg_name in ("tiny", "small") else 2
+        r = cpu_reference_run(cfg_name, max(1, a.steps), a.warmup, chunk, dtype_name, full_batch=batch, budget_s=240.0)
+        if r["images_per_step"] != batch:
+            # the bounded sample is smaller than the GPU arm's step: say what was run, not what the GPU arm runs
+            base_cfg = dict(base_cfg)
+            base_cfg.update({"workload": "LW-DETR-%s forward on the host CPU, %d images per step (bounded sample of the batch-%d/GPU workload; the forward is "
+                                         "per-image independent), 640x640 synthetic, random-init weights" % (cfg_name, r["images_per_step"], batch),
+                             "per_gpu_batch": r["images_per_step"], "global_batch": r["images_per_step"], "gpu_workload_batch": batch})
         print(json.dumps({
             "impl": "reference", "metric": "images/sec (640x640)", "value": r["value"], "unit": "images/s", "n_gpus": a.gpus,
             "steps": max(1, a.steps), "warmup": a.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
@@ -370,7 +411,7 @@ def main():
     cpu = None
     if rank == 0 and world == 1:
         try:
-            cpu = cpu_reference_run(cfg_name, 2, 1, 2 if cfg_name in ("tiny", "small") else 1, dtype_name)
+            cpu = cpu_reference_run(cfg_name, 2, 1, 4 if cfg_name in ("tiny", "small") else 2, dtype_name)
             cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
         except Exception as ex:
             cpu = {"error": repr(ex)}

@@ -66,22 +66,52 @@ LWDETR_API int lwdetr_attention(int dtype, const void* q, int ldq, const void* k
                                 void* out, int ldo, int nseq, int seqlen, int heads, int dh, float scale,
                                 void* stream);
 
-/* Multi-scale deformable attention forward.  Reference operator replaced:
- *   MSDA.ms_deform_attn_forward(value, spatial_shapes, level_start_index, sampling_loc, attn_weight,
- *   im2col_step) -> [B, Lq, M*D]   (models/ops/src/ms_deform_attn.h:19-35, vision.cpp:13-16,
- *   cuda/ms_deform_attn_cuda.cu:20-80, cuda/ms_deform_im2col_cuda.cuh:237-299)
- * fused with the softmax and sampling-location arithmetic of MSDeformAttn.forward
- * (ops/modules/ms_deform_attn.py:118-131), so it takes the RAW projections:
- *   value        16-bit [B, S, ldv]   (head m, channel c at column m*16 + c; D = 16)
+/* Multi-scale deformable attention forward with the REFERENCE OPERATOR'S OWN INTERFACE:
+ *   MultiScaleDeformableAttention.ms_deform_attn_forward(value, spatial_shapes, level_start_index, sampling_loc,
+ *   attn_weight, im2col_step) -> [B, Lq, M*D]
+ *   (models/ops/src/ms_deform_attn.h:19-35, vision.cpp:13-16, cuda/ms_deform_attn_cuda.cu:20-80,
+ *   cuda/ms_deform_im2col_cuda.cuh:33-84,237-299; Python caller functions/ms_deform_attn_func.py:28-38).
+ * All pointers DEVICE, contiguous, as the reference asserts (ms_deform_attn_cuda.cu:28-38):
+ *   value [B, S, M, D], sampling_loc [B, Lq, M, L, P, 2] (x, y normalised), attn_weight [B, Lq, M, L, P] and
+ *   out [B, Lq, M*D] share one element type `etype` (LWDETR_ET_F32 / _F16 / _BF16 - the reference compiles float and
+ *   double only, ms_deform_attn_cuda.cu:64); spatial_shapes int64 [L, 2] (H, W) and level_start_index int64 [L] are
+ *   DEVICE tensors exactly as the reference receives them.  Any D; D % 4 == 0 (fp32) / D % 8 == 0 (16-bit) with
+ *   16-byte aligned value / out takes the vectorised kernel, everything else a one-thread-per-channel kernel.
+ * Differences from the reference: the caller owns `out` (the reference allocates at::zeros, :54); every element of out
+ * is written, so it need not be zeroed; there is no im2col_step batching loop, but the reference's precondition
+ * B % min(B, im2col_step) == 0 (:50-52) is still checked so that the error behaviour matches. */
+enum { LWDETR_ET_F32 = 0, LWDETR_ET_F16 = 1, LWDETR_ET_BF16 = 2 };
+LWDETR_API int lwdetr_ms_deform_attn_forward(int etype, const void* value, const int64_t* spatial_shapes,
+                                             const int64_t* level_start_index, const void* sampling_loc,
+                                             const void* attn_weight, void* out, int B, int S, int M, int D, int Lq,
+                                             int L, int P, int im2col_step, void* stream);
+
+/* Backward of the same operator, fp32 (ms_deform_attn.h:37-60, ms_deform_attn_cuda.cu:83-154, cuh:301-920):
+ *   MSDA.ms_deform_attn_backward(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, grad_output,
+ *   im2col_step) -> [grad_value, grad_sampling_loc, grad_attn_weight].
+ * grad_output [B, Lq, M*D]; grad_value [B, S, M, D] is zeroed by the call (the reference returns at::zeros_like, :120) and
+ * accumulated with atomicAdd as in the reference; grad_sampling_loc [B, Lq, M, L, P, 2] and grad_attn_weight
+ * [B, Lq, M, L, P] are written once per element.  Caller-owned, stream-ordered. */
+LWDETR_API int lwdetr_ms_deform_attn_backward(const float* value, const int64_t* spatial_shapes, const int64_t* level_start_index,
+                                              const float* sampling_loc, const float* attn_weight, const float* grad_output,
+                                              float* grad_value, float* grad_sampling_loc, float* grad_attn_weight, int B, int S,
+                                              int M, int D, int Lq, int L, int P, int im2col_step, void* stream);
+
+/* The fused form the model schedules (same arithmetic, fewer bytes): the softmax over the L*P attention logits and the
+ * sampling-location arithmetic of MSDeformAttn.forward (ops/modules/ms_deform_attn.py:118-131, 4-d reference boxes) run
+ * inside the kernel, which therefore takes the RAW projections, and the value tensor is HEAD-MAJOR so that everything one
+ * (image, head) can sample is one contiguous slab streamed through shared memory (csrc/msda.cu):
+ *   value_hm     16-bit, element (b, m, s, c) at b*v_image_stride + (m*S + s)*16 + c   (D = 16)
  *   offs_logits  16-bit [B*Lq, ld_ol] = [M*L*P*2 sampling offsets | M*L*P attention logits]
  *   ref          fp32   [B*Lq, 4]     reference boxes (cx, cy, w, h)
+ *   valid_ratio  fp32   [B, L, 2] (w, h) or NULL: per-level valid ratios of a padded batch
+ *                (transformer.py:189-196, 352-353)
  *   spatial_shapes int32 [L, 2] (H, W) and level_start_index int32 [L] on the HOST
- *   out          16-bit [B*Lq, ld_out]
- * Unlike the reference there is no im2col_step batching loop and no device-side shape tensors. */
-LWDETR_API int lwdetr_msda_forward(int dtype, const void* value, int ldv, const void* offs_logits, int ld_ol,
-                                   const float* ref, void* out, int ld_out, int B, int S, int Lq, int M, int L,
-                                   int P, const int32_t* spatial_shapes_host, const int32_t* level_start_host,
-                                   void* stream);
+ *   out          16-bit [B*Lq, ld_out] */
+LWDETR_API int lwdetr_msda_forward(int dtype, const void* value_hm, int64_t v_image_stride, const void* offs_logits,
+                                   int ld_ol, const float* ref, const float* valid_ratio, void* out, int ld_out, int B,
+                                   int S, int Lq, int M, int L, int P, const int32_t* spatial_shapes_host,
+                                   const int32_t* level_start_host, void* stream);
 
 /* torch.topk(score, k, dim=1)[1] for fp32 score [B, S] -> int32 idx [B, k], sorted, ties -> lower index
  * (transformer.py:246). */

@@ -23,7 +23,9 @@ _SIGNATURES = {
     "lwdetr_conv3x3": (_i, [_i, _vp, _i, _i, _i, _i, _i, _i, _vp, _i, _vp, _i, _vp, _i, _vp]),
     "lwdetr_layernorm": (_i, [_i, _vp, _i, _vp, _i, _vp, _vp, _f, _i64, _i, _vp]),
     "lwdetr_attention": (_i, [_i, _vp, _i, _vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _i, _f, _vp]),
-    "lwdetr_msda_forward": (_i, [_i, _vp, _i, _vp, _i, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
+    "lwdetr_ms_deform_attn_forward": (_i, [_i, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
+    "lwdetr_ms_deform_attn_backward": (_i, [_vp] * 9 + [_i] * 8 + [_vp]),
+    "lwdetr_msda_forward": (_i, [_i, _vp, _i64, _vp, _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
     "lwdetr_topk": (_i, [_vp, _i, _i, _i, _vp, _vp]),
     "lwdetr_postprocess": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     "lwdetr_host_bicubic": (_i, [_vp, _i, _i, _i, _vp]),
@@ -124,18 +126,73 @@ def attention(q, k, v, out, nseq, seqlen, heads, dh, scale):
     return out
 
 
-def msda_forward(value, offs_logits, ref, out, B, S, Lq, M, L, P, shapes):
-    """value [B*S, ldv] view, offs_logits [B*Lq, 3*M*L*P], ref fp32 [B*Lq, 4], out [B*Lq, M*16]."""
+def value_to_head_major(value, B, S, M):
+    """[B*S, M*16] token-major (view, any row stride) -> contiguous head-major [B, M, S, 16] (what value_proj's epilogue writes)."""
+    return value.reshape(B, S, M, 16).permute(0, 2, 1, 3).contiguous()
+
+
+def msda_forward(value_hm, offs_logits, ref, out, B, S, Lq, M, L, P, shapes, valid_ratio=None, v_image_stride=None):
+    """value_hm head-major [B, M, S, 16], offs_logits [B*Lq, 3*M*L*P], ref fp32 [B*Lq, 4], out [B*Lq, M*16]."""
     sh = (ctypes.c_int32 * (2 * L))(*[v for hw in shapes for v in hw])
     starts, acc = [], 0
     for h, w in shapes:
         starts.append(acc)
         acc += h * w
     st = (ctypes.c_int32 * L)(*starts)
-    check(lib().lwdetr_msda_forward(dtype_code(value.dtype), ptr(value), value.stride(0), ptr(offs_logits),
-                                    offs_logits.stride(0), ptr(ref), ptr(out), out.stride(0), B, S, Lq, M, L, P,
+    stride = M * S * 16 if v_image_stride is None else v_image_stride
+    check(lib().lwdetr_msda_forward(dtype_code(value_hm.dtype), ptr(value_hm), stride, ptr(offs_logits),
+                                    offs_logits.stride(0), ptr(ref), ptr(valid_ratio), ptr(out), out.stride(0), B, S, Lq, M, L, P,
                                     ctypes.cast(sh, _vp), ctypes.cast(st, _vp), stream_ptr()), "lwdetr_msda_forward")
     return out
+
+
+ET_F32, ET_F16, ET_BF16 = 0, 1, 2
+
+
+def ms_deform_attn_forward(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, im2col_step=64):
+    """The reference operator (ms_deform_attn_func.py:28-38 -> MSDA.ms_deform_attn_forward): value [B,S,M,D],
+    spatial_shapes int64 [L,2], level_start_index int64 [L], sampling_loc [B,Lq,M,L,P,2], attn_weight [B,Lq,M,L,P], all
+    CUDA and contiguous; returns [B, Lq, M*D] in value's dtype (fp32, fp16 or bf16)."""
+    import torch
+    et = {torch.float32: ET_F32, torch.float16: ET_F16, torch.bfloat16: ET_BF16}.get(value.dtype)
+    if et is None:
+        raise RuntimeError("ms_deform_attn_forward: value must be float32, float16 or bfloat16, got %s" % value.dtype)
+    for name, t in (("value", value), ("spatial_shapes", spatial_shapes), ("level_start_index", level_start_index),
+                    ("sampling_loc", sampling_loc), ("attn_weight", attn_weight)):
+        if not t.is_cuda:
+            raise RuntimeError("ms_deform_attn_forward: %s must be a CUDA tensor (Not implemented on the CPU)" % name)   # ms_deform_attn.h:34
+        if not t.is_contiguous():
+            raise RuntimeError("ms_deform_attn_forward: %s tensor has to be contiguous" % name)                          # ms_deform_attn_cuda.cu:28-32
+    if sampling_loc.dtype != value.dtype or attn_weight.dtype != value.dtype:
+        raise RuntimeError("ms_deform_attn_forward: value, sampling_loc and attn_weight must share one dtype")
+    if spatial_shapes.dtype != torch.int64 or level_start_index.dtype != torch.int64:
+        raise RuntimeError("ms_deform_attn_forward: spatial_shapes / level_start_index must be int64")
+    B, S, M, D = value.shape
+    Lq, L, P = sampling_loc.shape[1], sampling_loc.shape[3], sampling_loc.shape[4]
+    out = torch.empty(B, Lq, M * D, device=value.device, dtype=value.dtype)
+    check(lib().lwdetr_ms_deform_attn_forward(et, ptr(value), ptr(spatial_shapes), ptr(level_start_index), ptr(sampling_loc),
+                                              ptr(attn_weight), ptr(out), B, S, M, D, Lq, L, P, int(im2col_step), stream_ptr()),
+          "lwdetr_ms_deform_attn_forward")
+    return out
+
+
+def ms_deform_attn_backward(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, grad_output, im2col_step=64):
+    """MSDA.ms_deform_attn_backward (ms_deform_attn.h:37-60): fp32 CUDA tensors -> (grad_value, grad_sampling_loc, grad_attn_weight)."""
+    import torch
+    for name, t in (("value", value), ("sampling_loc", sampling_loc), ("attn_weight", attn_weight), ("grad_output", grad_output)):
+        if not t.is_cuda:
+            raise RuntimeError("ms_deform_attn_backward: %s must be a CUDA tensor (Not implemented on the CPU)" % name)
+        if t.dtype != torch.float32:
+            raise RuntimeError("ms_deform_attn_backward: %s must be float32" % name)
+        if not t.is_contiguous():
+            raise RuntimeError("ms_deform_attn_backward: %s tensor has to be contiguous" % name)
+    B, S, M, D = value.shape
+    Lq, L, P = sampling_loc.shape[1], sampling_loc.shape[3], sampling_loc.shape[4]
+    gv, gl, ga = torch.empty_like(value), torch.empty_like(sampling_loc), torch.empty_like(attn_weight)
+    check(lib().lwdetr_ms_deform_attn_backward(ptr(value), ptr(spatial_shapes), ptr(level_start_index), ptr(sampling_loc), ptr(attn_weight),
+                                               ptr(grad_output), ptr(gv), ptr(gl), ptr(ga), B, S, M, D, Lq, L, P, int(im2col_step),
+                                               stream_ptr()), "lwdetr_ms_deform_attn_backward")
+    return gv, gl, ga
 
 
 def topk(score, k):

@@ -341,18 +341,15 @@ template <typename T, int DH>
 static int launch_short(const AttnArgs& a, cudaStream_t st) {
   constexpr int LDS = DH + 8;
   const size_t smem = static_cast<size_t>(3) * (112 + 256) * LDS * sizeof(T);
-  static int ctas_per_sm = 0;
+  if (int e = ensure_max_dyn_smem(reinterpret_cast<const void*>(attn_short_kernel<T, DH>), 200 * 1024)) return e;
+  static int ctas_per_sm = 0;   // a property of the kernel image and the sm_100a SM, identical on every device of a B200 box
   if (!ctas_per_sm) {
-    cudaError_t e = cudaFuncSetAttribute(attn_short_kernel<T, DH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    if (e != cudaSuccess) return static_cast<int>(e);
     int n = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, attn_short_kernel<T, DH>, 7 * 32, smem);
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, attn_short_kernel<T, DH>, 7 * 32, smem);
     if (e != cudaSuccess) return static_cast<int>(e);
     ctas_per_sm = n > 0 ? n : 1;
   }
-  int dev = 0, sms = 148;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int sms = current_device_sms();
   const long long items = static_cast<long long>(a.nseq) * a.heads;
   const unsigned grid = static_cast<unsigned>(std::min<long long>(items, static_cast<long long>(sms) * ctas_per_sm));
   launch_k(attn_short_kernel<T, DH>, dim3(grid), dim3(7 * 32), smem, st, a);
@@ -363,12 +360,7 @@ template <typename T, int DH, int WARPS>
 static int launch(const AttnArgs& a, cudaStream_t st) {
   constexpr int LDS = DH + 8;
   const size_t smem = static_cast<size_t>(WARPS * 16 + 2 * NSTAGE * KC) * LDS * sizeof(T);
-  static bool attr = false;
-  if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(attn_kernel<T, DH, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-    if (e != cudaSuccess) return static_cast<int>(e);
-    attr = true;
-  }
+  if (int e = ensure_max_dyn_smem(reinterpret_cast<const void*>(attn_kernel<T, DH, WARPS>), 96 * 1024)) return e;
   dim3 grid((a.seqlen + WARPS * 16 - 1) / (WARPS * 16), a.heads, a.nseq);
   launch_k(attn_kernel<T, DH, WARPS>, dim3(grid), dim3(WARPS * 32), smem, st, a);
   return static_cast<int>(cudaGetLastError());

@@ -410,12 +410,7 @@ static int launch_tc_m(const AttnArgs& a, int C, cudaStream_t st) {
   // second CTA can never become resident and spin inside tcgen05.alloc.
   const size_t need = 1024 + static_cast<size_t>(TC_QT + TC_KS + TC_VS) * 128 * DH * 2 + 512 + 2 * 2 * 2 * 128 * sizeof(float);
   const size_t smem = std::max<size_t>(need, 116 * 1024);
-  static bool attr = false;
-  if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(attn_tc_kernel<T, DH, POLY_MASK>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    if (e != cudaSuccess) return static_cast<int>(e);
-    attr = true;
-  }
+  if (int e = ensure_max_dyn_smem(reinterpret_cast<const void*>(attn_tc_kernel<T, DH, POLY_MASK>), 200 * 1024)) return e;
   dim3 grid((a.seqlen + TC_QT * TC_BM - 1) / (TC_QT * TC_BM), a.heads, a.nseq);
   launch_k(attn_tc_kernel<T, DH, POLY_MASK>, dim3(grid), dim3(TC_THREADS2), smem, st, tm, a, C);
   return static_cast<int>(cudaGetLastError());

@@ -2,6 +2,7 @@
 #include "lwdetr_b200.h"
 
 #include <cuda_runtime.h>
+#include <stdint.h>
 
 #include <string>
 
@@ -90,16 +91,51 @@ int lwdetr_attention(int dtype, const void* q, int ldq, const void* k, int ldk, 
   return 0;
 }
 
-int lwdetr_msda_forward(int dtype, const void* value, int ldv, const void* offs_logits, int ld_ol, const float* ref, void* out,
-                        int ld_out, int B, int S, int Lq, int M, int L, int P, const int32_t* spatial_shapes_host,
-                        const int32_t* level_start_host, void* stream) {
-  if (!value || !offs_logits || !ref || !out || !spatial_shapes_host || !level_start_host) return fail("lwdetr_msda_forward: null pointer");
+int lwdetr_ms_deform_attn_forward(int etype, const void* value, const int64_t* spatial_shapes, const int64_t* level_start_index,
+                                  const void* sampling_loc, const void* attn_weight, void* out, int B, int S, int M, int D, int Lq, int L,
+                                  int P, int im2col_step, void* stream) {
+  if (!value || !spatial_shapes || !level_start_index || !sampling_loc || !attn_weight || !out) return fail("lwdetr_ms_deform_attn_forward: null pointer");
+  if (etype != LWDETR_ET_F32 && etype != LWDETR_ET_F16 && etype != LWDETR_ET_BF16) return fail("lwdetr_ms_deform_attn_forward: etype must be LWDETR_ET_F32, _F16 or _BF16");
+  if (B < 1 || S < 1 || M < 1 || D < 1 || Lq < 1 || L < 1 || P < 1) return fail("lwdetr_ms_deform_attn_forward: sizes must be positive");
+  if (im2col_step < 1 || B % (B < im2col_step ? B : im2col_step) != 0)
+    return fail("lwdetr_ms_deform_attn_forward: batch(" + std::to_string(B) + ") must divide im2col_step(" + std::to_string(im2col_step) + ")");   // ms_deform_attn_cuda.cu:50-52
+  lwb::MsdaOpArgs a{};
+  a.value = value; a.spatial_shapes = spatial_shapes; a.level_start_index = level_start_index; a.sampling_loc = sampling_loc;
+  a.attn_weight = attn_weight; a.out = out; a.B = B; a.S = S; a.M = M; a.D = D; a.Lq = Lq; a.L = L; a.P = P;
+  int e = lwb::msda_op_launch(etype, a, static_cast<cudaStream_t>(stream));
+  if (e == -2) return fail("lwdetr_ms_deform_attn_forward: unsupported element type / head dim");
+  if (e) return cuda_fail(e, "lwdetr_ms_deform_attn_forward launch");
+  return 0;
+}
+
+int lwdetr_ms_deform_attn_backward(const float* value, const int64_t* spatial_shapes, const int64_t* level_start_index, const float* sampling_loc,
+                                   const float* attn_weight, const float* grad_output, float* grad_value, float* grad_sampling_loc,
+                                   float* grad_attn_weight, int B, int S, int M, int D, int Lq, int L, int P, int im2col_step, void* stream) {
+  if (!value || !spatial_shapes || !level_start_index || !sampling_loc || !attn_weight || !grad_output || !grad_value || !grad_sampling_loc || !grad_attn_weight)
+    return fail("lwdetr_ms_deform_attn_backward: null pointer");
+  if (B < 1 || S < 1 || M < 1 || D < 1 || Lq < 1 || L < 1 || P < 1) return fail("lwdetr_ms_deform_attn_backward: sizes must be positive");
+  if (im2col_step < 1 || B % (B < im2col_step ? B : im2col_step) != 0)
+    return fail("lwdetr_ms_deform_attn_backward: batch(" + std::to_string(B) + ") must divide im2col_step(" + std::to_string(im2col_step) + ")");   // ms_deform_attn_cuda.cu:116-118
+  lwb::MsdaOpArgs a{};
+  a.value = value; a.spatial_shapes = spatial_shapes; a.level_start_index = level_start_index; a.sampling_loc = sampling_loc;
+  a.attn_weight = attn_weight; a.out = nullptr; a.B = B; a.S = S; a.M = M; a.D = D; a.Lq = Lq; a.L = L; a.P = P;
+  int e = lwb::msda_op_backward_launch(a, grad_output, grad_value, grad_sampling_loc, grad_attn_weight, static_cast<cudaStream_t>(stream));
+  if (e) return cuda_fail(e, "lwdetr_ms_deform_attn_backward launch");
+  return 0;
+}
+
+int lwdetr_msda_forward(int dtype, const void* value_hm, int64_t v_image_stride, const void* offs_logits, int ld_ol, const float* ref,
+                        const float* valid_ratio, void* out, int ld_out, int B, int S, int Lq, int M, int L, int P,
+                        const int32_t* spatial_shapes_host, const int32_t* level_start_host, void* stream) {
+  if (!value_hm || !offs_logits || !ref || !out || !spatial_shapes_host || !level_start_host) return fail("lwdetr_msda_forward: null pointer");
   if (L < 1 || L > lwb::MSDA_MAX_LEVELS) return fail("lwdetr_msda_forward: 1..4 levels supported");
-  if ((ldv % 8) || (ld_out % 8) || (ld_ol % 2)) return fail("lwdetr_msda_forward: misaligned leading dimension");
+  if ((ld_out % 8) || (ld_ol % 2) || (v_image_stride % 8) || (reinterpret_cast<uintptr_t>(value_hm) & 15)) return fail("lwdetr_msda_forward: misaligned leading dimension / base");
+  if (v_image_stride < static_cast<int64_t>(M) * S * lwb::MSDA_D) return fail("lwdetr_msda_forward: v_image_stride smaller than one image's M*S*16 values");
   lwb::MsdaArgs a{};
-  a.value = value; a.ldv = ldv; a.offs_logits = offs_logits; a.ld_ol = ld_ol; a.ref = ref; a.out = out; a.ld_out = ld_out;
-  a.batch = B; a.nq = Lq; a.heads = M; a.levels = L; a.points = P; a.S = S;
+  a.value = value_hm; a.v_b_stride = v_image_stride; a.offs_logits = offs_logits; a.ld_ol = ld_ol; a.ref = ref; a.valid_ratio = valid_ratio;
+  a.out = out; a.ld_out = ld_out; a.batch = B; a.nq = Lq; a.heads = M; a.levels = L; a.points = P; a.S = S;
   for (int l = 0; l < L; ++l) { a.lvl_h[l] = spatial_shapes_host[2 * l]; a.lvl_w[l] = spatial_shapes_host[2 * l + 1]; a.lvl_start[l] = level_start_host[l]; }
+  if (lwb::msda_plan(&a)) return fail("lwdetr_msda_forward: a feature level is wider than 840 tokens or there are too many bands");
   int e = lwb::msda_launch(dtype, a, static_cast<cudaStream_t>(stream));
   if (e == -2) return fail("lwdetr_msda_forward: unsupported (levels, points) combination");
   if (e) return cuda_fail(e, "lwdetr_msda_forward launch");

@@ -407,6 +407,8 @@ int Engine::plan(int B, std::string* err) {
     S += lvl_hw[l] * lvl_hw[l];
   }
   const long long BS = 1LL * B * S, BQ = 1LL * B * nq;
+  const int ldc = static_cast<int>(align_up(static_cast<size_t>(ncls), 32));   // row pitch of the fp32 class-logit buffers
+  ldc_ = ldc;
   if (d / M != 16) { *err = "deformable attention head dim must be 16"; return -1; }
   if (C / heads != 16 && C / heads != 32 && C / heads != 64) { *err = "unsupported ViT head dim"; return -1; }
 
@@ -424,6 +426,7 @@ int Engine::plan(int B, std::string* err) {
       const float* gamma = nullptr; Mat resid{nullptr, 0}; int resid_mod = 0; int act = ACT_NONE; int out_fp32 = 0;
       int rows_in = ROWS_PLAIN, remap = 0, shuffle = 0, IH = 0, IW = 0;
       int conv = 0, cB = 0, cOH = 0, cOW = 0;   // conv: 1 = 3x3 s1, 2 = 3x3 s2
+      int hm_S = 0, hm_heads = 0, hm_slices = 0; const uint8_t* row_zero = nullptr;
       float2* stats_out = nullptr; const float2* stats_in = nullptr; int ln_C = 0; float ln_eps = 0.f;
     };
     int stats_parts = 0;   // partial (sum, sumsq) pairs per row written by the N = C producer GEMMs
@@ -436,6 +439,7 @@ int Engine::plan(int B, std::string* err) {
       g.gamma = o.gamma; g.resid = o.resid.p; g.ld_resid = o.resid.ld; g.resid_mod = o.resid_mod; g.act = o.act;
       g.out = out; g.ld_out = ld_out; g.out_fp32 = o.out_fp32; g.rows_in = o.rows_in; g.remap_rows = o.remap;
       g.shuffle_cout = o.shuffle; g.IH = o.IH; g.IW = o.IW;
+      g.hm_S = o.hm_S; g.hm_heads = o.hm_heads; g.hm_slices = o.hm_slices; g.row_zero = o.row_zero;
       if (o.conv) { g.a_mode = o.conv == 1 ? AMODE_CONV3_S1 : AMODE_CONV3_S2; g.B = o.cB; g.OH = o.cOH; g.OW = o.cOW; }
       g.stats_out = o.stats_out; g.stats_in = o.stats_in; g.stats_parts_in = stats_parts; g.ln_C = o.ln_C; g.ln_eps = o.ln_eps;
       if (o.stats_in) g.colsum = w32(wkey + ".cs");
@@ -449,7 +453,7 @@ int Engine::plan(int B, std::string* err) {
       Op P_;
       P_.label = label;
       P_.run = [op](cudaStream_t st) { return gemm_launch(op, st); };
-      P_.out = out; P_.rows = out_rows >= 0 ? out_rows : (o.shuffle ? Mrows * 4 : Mrows); P_.cols = o.shuffle ? o.shuffle : N;
+      P_.out = out; P_.rows = out_rows >= 0 ? out_rows : (o.shuffle ? Mrows * 4 : Mrows); P_.cols = o.shuffle ? o.shuffle : (o.hm_S ? 16 : N);
       P_.ld = ld_out; P_.fp32 = o.out_fp32;
       P_.flops = op.flops;
       P_.bytes = 2.0 * (static_cast<double>(Mrows) * K + static_cast<double>(N) * K) + (o.out_fp32 ? 4.0 : 2.0) * Mrows * N + (o.resid.p ? 2.0 * Mrows * N : 0.0);
@@ -602,8 +606,9 @@ int Engine::plan(int B, std::string* err) {
     }
 
     // ================================================================ two-stage query selection
+    // value_proj of all decoder layers, HEAD-MAJOR [B][layer][head][S][16] (msda.cu stages whole (image, head) slabs)
     Mat value = buf16(BS, NL * d), om = buf16(BS, d), omn = buf16(BS, d);
-    float* cls_all = buf32(BS * 96);
+    float* cls_all = buf32(BS * ldc);
     float* score = buf32(BS);
     int* topk_idx = static_cast<int*>(salloc(static_cast<size_t>(BQ) * 4));
     Mat sel = buf16(BQ, d), h1 = buf16(BQ, d), h2 = buf16(BQ, d);
@@ -612,12 +617,12 @@ int Engine::plan(int B, std::string* err) {
     float* enc_boxes = buf32(BQ * 4);
     float* refpoint = buf32(BQ * 4);
     Mat sine = buf16(BQ, 2 * d), qpos = buf16(BQ, d);
-    add_gemm("value_proj", memory, BS, d, "value", NL * d, value.p, value.ld, GemmOpt{});
+    { GemmOpt o; o.hm_S = S; o.hm_heads = M; o.hm_slices = NL; add_gemm("value_proj", memory, BS, d, "value", NL * d, value.p, 16, o, BS * NL * M); }
     add_gemm("enc_output", memory, BS, d, "enc_out", d, om.p, om.ld, GemmOpt{});
     add_ln("enc_output_norm", om, omn, "enc_ln", 1e-5f, BS, d, pass ? static_cast<const uint8_t*>(w16("invalid")) : nullptr, S,
            pass ? w32("enc_out.b") : nullptr);
-    { GemmOpt o; o.out_fp32 = 1; add_gemm("enc_class", omn, BS, d, "enc_cls", ncls, cls_all, 96, o); }
-    add_op("enc_score", [cls_all, ncls, score, BS](cudaStream_t st) { return rowmax_launch(cls_all, 96, ncls, score, BS, st); }, score, BS, 1, 1, 1, 4.0 * BS * ncls);
+    { GemmOpt o; o.out_fp32 = 1; add_gemm("enc_class", omn, BS, d, "enc_cls", ncls, cls_all, ldc, o); }
+    add_op("enc_score", [cls_all, ncls, ldc, score, BS](cudaStream_t st) { return rowmax_launch(cls_all, ldc, ncls, score, BS, st); }, score, BS, 1, 1, 1, 4.0 * BS * ncls);
     add_op("topk", [this, score, B, S, nq, topk_idx](cudaStream_t st) {
       if (in_topk_override_ != nullptr)
         return static_cast<int>(cudaMemcpyAsync(topk_idx, in_topk_override_, static_cast<size_t>(B) * nq * 4, cudaMemcpyDeviceToDevice, st));
@@ -625,8 +630,8 @@ int Engine::plan(int B, std::string* err) {
     }, nullptr, 0, 0, 0, 0, 4.0 * BS);
     {
       void* omp = omn.p; void* selp = sel.p;
-      add_op("gather_topk", [omp, d, cls_all, ncls, topk_idx, B, S, nq, selp, enc_logits, dt](cudaStream_t st) {
-        return gather_topk_launch(dt, omp, d, cls_all, 96, ncls, topk_idx, B, S, nq, d, selp, enc_logits, st);
+      add_op("gather_topk", [omp, d, cls_all, ncls, ldc, topk_idx, B, S, nq, selp, enc_logits, dt](cudaStream_t st) {
+        return gather_topk_launch(dt, omp, d, cls_all, ldc, ncls, topk_idx, B, S, nq, d, selp, enc_logits, st);
       }, sel.p, BQ, d, d, 0, 4.0 * BQ * d);
     }
     { GemmOpt o; o.act = ACT_RELU; add_gemm("enc_box0", sel, BQ, d, "enc_box0", d, h1.p, h1.ld, o); }
@@ -653,9 +658,10 @@ int Engine::plan(int B, std::string* err) {
     }
     MsdaArgs mbase;
     std::memset(&mbase, 0, sizeof mbase);
-    mbase.ldv = value.ld; mbase.offs_logits = oa.p; mbase.ld_ol = oa.ld; mbase.ref = refpoint; mbase.out = ms.p; mbase.ld_out = ms.ld;
+    mbase.v_b_stride = 1LL * NL * M * S * MSDA_D; mbase.offs_logits = oa.p; mbase.ld_ol = oa.ld; mbase.ref = refpoint; mbase.out = ms.p; mbase.ld_out = ms.ld;
     mbase.batch = B; mbase.nq = nq; mbase.heads = M; mbase.levels = L; mbase.points = P; mbase.S = S;
     for (int l = 0; l < L; ++l) { mbase.lvl_h[l] = lvl_hw[l]; mbase.lvl_w[l] = lvl_hw[l]; mbase.lvl_start[l] = lvl_start[l]; }
+    if (msda_plan(&mbase)) { *err = "deformable attention: a feature level is too wide to stage"; return -1; }
     Mat cur = tgt;
     for (int i = 0; i < NL; ++i) {
       const std::string k = "dec" + std::to_string(i) + ".", lb = "dec" + std::to_string(i);
@@ -667,7 +673,7 @@ int Engine::plan(int B, std::string* err) {
       add_gemm(lb + ".offs_attn", tq, BQ, d, k + "oa", 3 * M * L * P, oa.p, oa.ld, GemmOpt{});
       {
         MsdaArgs ma = mbase;
-        ma.value = cptr(value.p) + static_cast<size_t>(i) * d * 2;
+        ma.value = cptr(value.p) + static_cast<size_t>(i) * M * S * MSDA_D * 2;
         add_op(lb + ".msda", [ma, dt](cudaStream_t st) { return msda_launch(dt, ma, st); }, ms.p, BQ, d, d, 0,
                2.0 * std::min<double>(1.0 * BS * d, 1.0 * BQ * M * L * P * 4 * 16) + 2.0 * BQ * M * L * P * 3 + 2.0 * BQ * d);
       }
@@ -681,11 +687,11 @@ int Engine::plan(int B, std::string* err) {
       add_ln(lb + ".hs", tgt, hsl, "dec_norm", 1e-5f, BQ, d);
     }
     // ================================================================ heads
-    float* logits = buf32(NL * BQ * 96);
+    float* logits = buf32(NL * BQ * ldc);
     float* delta = buf32(NL * BQ * 4);
     float* boxes = buf32(NL * BQ * 4);
     Mat bh1 = buf16(NL * BQ, d), bh2 = buf16(NL * BQ, d);
-    { GemmOpt o; o.out_fp32 = 1; add_gemm("class_embed", hs, NL * BQ, d, "cls", ncls, logits, 96, o); }
+    { GemmOpt o; o.out_fp32 = 1; add_gemm("class_embed", hs, NL * BQ, d, "cls", ncls, logits, ldc, o); }
     { GemmOpt o; o.act = ACT_RELU; add_gemm("bbox0", hs, NL * BQ, d, "box0", d, bh1.p, bh1.ld, o); }
     { GemmOpt o; o.act = ACT_RELU; add_gemm("bbox1", bh1, NL * BQ, d, "box1", d, bh2.p, bh2.ld, o); }
     { GemmOpt o; o.out_fp32 = 1; add_gemm("bbox2", bh2, NL * BQ, d, "box2", 4, delta, 4, o); }
@@ -773,7 +779,7 @@ int Engine::forward(const void* images, int images_fp32, int B, float* pred_logi
   const int nq = cfg_.num_queries, ncls = cfg_.num_classes, NL = cfg_.dec_layers;
   const long long BQ = 1LL * B * nq;
   auto copy_logits = [&](float* dst, int layer) {
-    return cudaMemcpy2DAsync(dst, ncls * 4, out_logits_ + static_cast<size_t>(layer) * BQ * 96, 96 * 4, ncls * 4, static_cast<size_t>(BQ), cudaMemcpyDeviceToDevice, st);
+    return cudaMemcpy2DAsync(dst, ncls * 4, out_logits_ + static_cast<size_t>(layer) * BQ * ldc_, static_cast<size_t>(ldc_) * 4, ncls * 4, static_cast<size_t>(BQ), cudaMemcpyDeviceToDevice, st);
   };
   cudaError_t e = cudaSuccess;
   if (pred_logits) e = copy_logits(pred_logits, NL - 1);

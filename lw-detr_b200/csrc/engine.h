@@ -90,7 +90,8 @@ class Engine {
   int in_images_fp32_ = 1;
   const int32_t* in_topk_override_ = nullptr;
   // result buffers (engine owned)
-  float* out_logits_ = nullptr;   // [layers, B, nq, 96]
+  float* out_logits_ = nullptr;   // [layers, B, nq, ldc_]
+  int ldc_ = 96;                  // row pitch of the class-logit buffers: num_classes rounded up to 32
   float* out_boxes_ = nullptr;    // [layers, B, nq, 4]
   float* out_enc_logits_ = nullptr;  // [B, nq, ncls]
   float* out_enc_boxes_ = nullptr;   // [B, nq, 4]

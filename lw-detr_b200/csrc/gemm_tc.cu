@@ -254,6 +254,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       long long out_row = m;
       if (GEN && p.remap_rows) out_row = (static_cast<long long>(b) * p.IH + y) * p.IW + x;
       const long long res_row = p.resid_mod > 0 ? (m % p.resid_mod) : m;
+      const bool zero_row = GEN && p.row_zero != nullptr && valid && __ldg(p.row_zero + m) != 0;
 
       const int npad = p.n_tiles * BN;
       const float* s_bias = s_vec + n0;
@@ -328,9 +329,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           for (int j = 0; j < 16; ++j)
             if (j < nrem) v[j] += Cvt<T>::to_f(resid_row[n + j]);
         }
+        if (GEN && zero_row) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = 0.f;
+        }
         // destination
         long long orow = out_row;
         int ocol = n;
+        if (GEN && p.hm_S > 0) {                      // head-major: one 16-column chunk = one (slice, head), ld_out == 16
+          const int dd = p.hm_heads * 16;
+          const int slice = n / dd, head = (n - slice * dd) >> 4;
+          const int bb = m / p.hm_S, ss = m - bb * p.hm_S;
+          orow = ((static_cast<long long>(bb) * p.hm_slices + slice) * p.hm_heads + head) * p.hm_S + ss;
+          ocol = 0;
+        }
         if (GEN && p.shuffle_cout > 0) {
           const int q = n / p.shuffle_cout;
           ocol = n - q * p.shuffle_cout;
@@ -451,14 +463,7 @@ static int encode(CUtensorMap* tm, int dtype, int rank, const void* base, const 
   return tma_encode(tm, dtype, rank, base, dims, strides_bytes, box, 128, err);
 }
 
-static int num_sms() {
-  static int n = [] {
-    int dev = 0, v = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = 148;
-    return v;
-  }();
-  return n;
-}
+static int num_sms() { return current_device_sms(); }
 
 static int pick_bn(int N, int m_tiles) {
   int bn;
@@ -493,6 +498,13 @@ int gemm_build(const GemmDesc& d, GemmOp* op, std::string* err) {
   a.bias = d.bias; a.gamma = d.gamma; a.resid = d.resid; a.ld_resid = d.ld_resid; a.resid_mod = d.resid_mod;
   a.act = d.act; a.out = d.out; a.ld_out = d.ld_out; a.out_fp32 = d.out_fp32;
   a.rows_in = d.rows_in; a.remap_rows = d.remap_rows; a.shuffle_cout = d.shuffle_cout; a.IH = d.IH; a.IW = d.IW;
+  a.hm_S = d.hm_S; a.hm_heads = d.hm_heads; a.hm_slices = d.hm_slices; a.row_zero = d.row_zero;
+  if (d.hm_S > 0) {
+    if (d.a_mode != AMODE_PLAIN || d.remap_rows || d.shuffle_cout || d.out_fp32 || d.hm_heads < 1 || d.hm_slices < 1 ||
+        d.N != d.hm_slices * d.hm_heads * 16 || d.M % d.hm_S != 0) { *err = "gemm: head-major store needs a plain 16-bit GEMM with N == slices*heads*16 and M % S == 0"; return -1; }
+    a.ld_out = 16;
+  }
+  if (d.out_fp32 && d.ld_out < d.N) { *err = "gemm: fp32 ld_out must be >= N"; return -1; }
   a.stats_out = d.stats_out; a.stats_in = d.stats_in; a.stats_parts_in = d.stats_parts_in; a.colsum = d.colsum;
   a.ln_inv_c = d.ln_C > 0 ? 1.f / d.ln_C : 0.f; a.ln_eps = d.ln_eps;
   if ((d.stats_out || d.stats_in) && (d.a_mode != AMODE_PLAIN || d.remap_rows || d.shuffle_cout || d.out_fp32)) { *err = "gemm: LN fusion needs a plain 16-bit GEMM"; return -1; }
@@ -579,18 +591,13 @@ int gemm_build(const GemmDesc& d, GemmOp* op, std::string* err) {
 
 template <typename T, int BN, int EP>
 static int launch_inst(const GemmOp& op, cudaStream_t st) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<T, BN, EP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
-    if (e != cudaSuccess) return static_cast<int>(e);
-    attr_set = true;
-  }
+  if (int e = ensure_max_dyn_smem(reinterpret_cast<const void*>(gemm_tc_kernel<T, BN, EP>), 226 * 1024)) return e;
   launch_k(gemm_tc_kernel<T, BN, EP>, dim3(op.grid), dim3(GEMM_THREADS), op.smem, st, op.ta, op.tb, op.args);
   return static_cast<int>(cudaGetLastError());
 }
 
 static int pick_ep(const GemmArgs& a) {
-  const bool special_rows = a.out_fp32 || a.remap_rows || a.shuffle_cout > 0;
+  const bool special_rows = a.out_fp32 || a.remap_rows || a.shuffle_cout > 0 || a.hm_S > 0 || a.row_zero != nullptr;
   if (special_rows) return EP_GENERIC;
   if (a.stats_in) {
     if (a.gamma || a.resid || a.stats_out) return EP_GENERIC;

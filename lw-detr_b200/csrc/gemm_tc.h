@@ -35,6 +35,10 @@ struct GemmArgs {
   int remap_rows;           // 1: write rows in spatial (b,y,x) order (needs rows_in grid IH x IW)
   int shuffle_cout;         // >0: ConvTranspose2d(k=2,s=2) pixel shuffle, n = (dy*2+dx)*cout + co
   int IH, IW;               // token grid per image for rows_in / shuffle (40 x 40 for the ViT)
+  // head-major store (the deformable-attention value tensor, msda.cu): hm_S > 0 writes element (row b*hm_S + s,
+  // column slice*hm_heads*16 + head*16 + c) to out[(((b*hm_slices + slice)*hm_heads + head)*hm_S + s)*16 + c]
+  int hm_S, hm_heads, hm_slices;
+  const uint8_t* row_zero;  // [M] or null: rows flagged non-zero are stored as zeros (padded memory tokens, ms_deform_attn.py:114-115)
   // LayerNorm fusion (ViT blocks).  Producer side: the epilogue also emits per-row partial (sum, sum of
   // squares) of the rounded output, one float2 per (row, n_tile, column half).  Consumer side: the GEMM runs
   // on the RAW rows and applies  out = rstd*(acc - mean*colsum[n]) + bias[n]  where the LN weight is folded into
@@ -65,6 +69,8 @@ struct GemmDesc {
   int ld_out = 0;
   int out_fp32 = 0;
   int rows_in = ROWS_PLAIN, remap_rows = 0, shuffle_cout = 0, IH = 0, IW = 0;
+  int hm_S = 0, hm_heads = 0, hm_slices = 0;   // head-major store (see GemmArgs)
+  const uint8_t* row_zero = nullptr;
   float2* stats_out = nullptr;          // producer: buffer with room for M * 2 * n_tiles float2
   const float2* stats_in = nullptr;     // consumer
   int stats_parts_in = 0;

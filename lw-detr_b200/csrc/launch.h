@@ -13,6 +13,11 @@ namespace lwb {
 
 int& pdl_enabled();   // defined in tma_util.cu; set through lwdetr_set_option(engine, "pdl", v)
 
+// Per-DEVICE one-time kernel attributes (tma_util.cu).  cudaFuncSetAttribute acts on the current device only, so the
+// "done" record is keyed by (kernel, device): a second GPU used from the same process gets its own opt-in.
+int ensure_max_dyn_smem(const void* kernel, int bytes);        // cudaFuncAttributeMaxDynamicSharedMemorySize
+int current_device_sms();                                      // SM count of the current device (cached per device)
+
 #ifdef __CUDACC__
 __device__ __forceinline__ void pdl_sync() {
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");

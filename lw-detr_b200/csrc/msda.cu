@@ -2,19 +2,288 @@
 // ms_deform_im2col_cuda.cuh:33-84 bilinear, :237-299 kernel, launcher :923-954; host glue
 // ms_deform_attn_cuda.cu:20-80; module math ops/modules/ms_deform_attn.py:118-131).
 //
-// B200 design: an HBM/L2 gather, no tensor cores.  The reference spends one thread per output
-// channel, re-reading the sampling location and weight D times and issuing scalar loads.  Here one
-// thread owns 8 channels of one (query, head): every bilinear corner is ONE 16-byte read-only load
-// (two adjacent threads cover the 32-byte head slice = one DRAM sector), the location arithmetic,
-// the softmax over the L*P logits of the head and the weighted accumulation stay in registers, and
-// the [B*nq, d] result is written with 16-byte coalesced stores.  The kernel consumes the raw
-// sampling_offsets / attention_weights projections directly (softmax and location math fused), so
-// the [B,nq,M,L,P,2] location tensor of the reference never exists in memory.
+// Two kernels, both HBM-bound byte movers without tensor cores:
+//
+// 1. msda_fwd_kernel - the model path.  The reference gathers 32-byte head slices from a token-major value tensor:
+//    every bilinear corner is a random DRAM sector.  Here value_proj writes the value tensor HEAD-MAJOR
+//    ([image][head][token][16], gemm_tc "head-major" epilogue), so everything one (image, head) can ever sample is
+//    ONE contiguous slab (51 KB at 40x40).  Persistent CTAs (one per SM) walk the (image, head) items: a producer
+//    warp streams the slab - in bands of <= 1680 tokens - into a 4-stage shared-memory ring with 1-D bulk copies
+//    (cp.async.bulk + mbarrier complete_tx), 19 consumer warps (thread = 8 channels of one query) take the bilinear
+//    corners out of shared memory.  DRAM sees the value tensor exactly once, as a linear stream; the softmax over
+//    the L*P logits, the sampling-location arithmetic (incl. valid ratios of padded batches) and the weighted sum
+//    stay in registers; the raw projections of the NEXT item are prefetched while the current one is sampled.
+//    A P3 level (80x80 = 205 KB per head) does not fit a stage: it is cut into bands of 21 rows (one halo row), each
+//    sample is handled by the band that holds both of its rows.
+//
+// 2. msda_op_kernel - the reference operator's own interface (token-major value [B,S,M,D], explicit sampling
+//    locations and attention weights, fp32 / fp16 / bf16, any D % 8 == 0): a direct gather, one thread = 8 (16-bit)
+//    or 4 (fp32) channels of one (query, head), 16-byte read-only loads, all L*P*4 corner loads issued before use.
 #include "msda.h"
 #include "launch.h"
 #include "ptx.cuh"
 
+#include <algorithm>
+
 namespace lwb {
+
+static constexpr int MS_STAGES = 4;
+static constexpr int MS_STAGE_TOKENS = 1680;                       // 21 rows of 80 / 42 rows of 40
+static constexpr int MS_STAGE_BYTES = MS_STAGE_TOKENS * MSDA_D * 2;
+static constexpr int MS_CONSUMER_WARPS = 19;                       // 608 threads = 304 queries x 2 channel halves; 20 warps in all => 96 registers/thread
+static constexpr int MS_QPASS = MS_CONSUMER_WARPS * 16;            // queries per pass
+static constexpr int MS_THREADS = 32 * (1 + MS_CONSUMER_WARPS);
+static constexpr int MS_SMEM = MS_STAGES * MS_STAGE_BYTES + 128;
+
+__device__ __forceinline__ U4 lds16(const void* p) {
+  U4 r;
+  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(smem_u32(p)));
+  return r;
+}
+
+template <typename T, int NL, int NP>   // levels, points per head and level
+__global__ void __launch_bounds__(MS_THREADS, 1) msda_fwd_kernel(const __grid_constant__ MsdaArgs p) {
+  constexpr int LP = NL * NP;
+  extern __shared__ __align__(128) uint8_t ms_smem[];
+  uint64_t* full = reinterpret_cast<uint64_t*>(ms_smem + MS_STAGES * MS_STAGE_BYTES);
+  uint64_t* empty = full + MS_STAGES;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < MS_STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], MS_CONSUMER_WARPS);
+    }
+    fence_mbar_init();
+  }
+  __syncthreads();
+  pdl_sync();   // programmatic dependent launch: release the successor, wait for the predecessor (launch.h)
+  const int nitems = p.batch * p.heads;
+  const int npass = (p.nq + MS_QPASS - 1) / MS_QPASS;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ------------------------------------------------------------------ producer: slabs -> shared-memory ring
+      uint32_t ring = 0;
+      for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+        const int b = item / p.heads, m = item - b * p.heads;
+        const T* slab = reinterpret_cast<const T*>(p.value) + static_cast<long long>(b) * p.v_b_stride + static_cast<long long>(m) * p.S * MSDA_D;
+        for (int pass = 0; pass < npass; ++pass)
+          for (int k = 0; k < p.nbands; ++k, ++ring) {
+            const int s = ring % MS_STAGES;
+            mbar_wait(&empty[s], ((ring / MS_STAGES) & 1) ^ 1);
+            mbar_arrive_expect_tx(&full[s], static_cast<uint32_t>(p.bands[k].bytes));
+            bulk_load(ms_smem + s * MS_STAGE_BYTES, slab + static_cast<long long>(p.bands[k].tok0) * MSDA_D, static_cast<uint32_t>(p.bands[k].bytes), &full[s]);
+          }
+      }
+    }
+    return;
+  }
+
+  // ---------------------------------------------------------------------- consumers: thread = 8 channels of one query
+  const int ct = threadIdx.x - 32;
+  const int qi = ct >> 1, half = ct & 1;
+  struct Raw {
+    uint32_t off[LP];          // (dx, dy) 16-bit pairs
+    uint32_t lg[LP / 2];       // logits, 16-bit pairs
+    float4 ref;
+  };
+  auto load_raw = [&](int item, int pass, Raw& r) {
+    const int b = item / p.heads, m = item - b * p.heads;
+    const int q = pass * MS_QPASS + qi;
+    if (item >= nitems || q >= p.nq) return;
+    const long long row = static_cast<long long>(b) * p.nq + q;
+    const T* oa = reinterpret_cast<const T*>(p.offs_logits) + row * p.ld_ol;
+    const uint32_t* o32 = reinterpret_cast<const uint32_t*>(oa + m * (2 * LP));
+#pragma unroll
+    for (int i = 0; i < LP; ++i) r.off[i] = __ldg(o32 + i);
+    const uint32_t* l32 = reinterpret_cast<const uint32_t*>(oa + p.heads * (2 * LP) + m * LP);
+#pragma unroll
+    for (int i = 0; i < LP / 2; ++i) r.lg[i] = __ldg(l32 + i);
+    r.ref = __ldg(reinterpret_cast<const float4*>(p.ref) + row);
+  };
+  Raw nxt;
+  load_raw(blockIdx.x, 0, nxt);
+  uint32_t ring = 0;
+  for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+    const int b = item / p.heads, m = item - b * p.heads;
+    for (int pass = 0; pass < npass; ++pass) {
+      const int q = pass * MS_QPASS + qi;
+      const bool active = q < p.nq;
+      const Raw cur = nxt;
+      if (pass + 1 < npass) load_raw(item, pass + 1, nxt);
+      else load_raw(item + gridDim.x, 0, nxt);
+      // ---- per-(query, head) sample table: image coordinates and softmax weight (0 when the sample is outside)
+      float px[LP], py[LP], pw[LP];
+      if (active) {
+        float mx = -INFINITY;
+#pragma unroll
+        for (int i = 0; i < LP / 2; ++i) {
+          const float2 f = Cvt<T>::unpack(cur.lg[i]);
+          pw[2 * i] = f.x;
+          pw[2 * i + 1] = f.y;
+          mx = fmaxf(mx, fmaxf(f.x, f.y));
+        }
+        float sum = 0.f;
+#pragma unroll
+        for (int i = 0; i < LP; ++i) {
+          pw[i] = __expf(pw[i] - mx);
+          sum += pw[i];
+        }
+        const float inv = 1.f / sum;
+        const float sx = cur.ref.z * (0.5f / NP), sy = cur.ref.w * (0.5f / NP);
+#pragma unroll
+        for (int i = 0; i < LP; ++i) {
+          const int l = i / NP;
+          const float2 o = Cvt<T>::unpack(cur.off[i]);
+          float lx = cur.ref.x + o.x * sx, ly = cur.ref.y + o.y * sy;      // ms_deform_attn.py:125-127
+          if (p.valid_ratio != nullptr) {                                  // transformer.py:352-353: boxes scaled per level
+            lx *= __ldg(p.valid_ratio + (b * NL + l) * 2);
+            ly *= __ldg(p.valid_ratio + (b * NL + l) * 2 + 1);
+          }
+          const int H = p.lvl_h[l], W = p.lvl_w[l];
+          px[i] = lx * W - 0.5f;                                           // cuh:285-286
+          py[i] = ly * H - 0.5f;
+          const bool in = py[i] > -1.f && px[i] > -1.f && py[i] < H && px[i] < W;   // cuh:288
+          pw[i] = in ? pw[i] * inv : 0.f;
+        }
+      }
+      float acc[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+      for (int k = 0; k < p.nbands; ++k, ++ring) {
+        const int s = ring % MS_STAGES;
+        const MsdaBand bd = p.bands[k];
+        mbar_wait(&full[s], (ring / MS_STAGES) & 1);
+        if (active) {
+          const uint8_t* stage = ms_smem + s * MS_STAGE_BYTES + half * 16;
+#pragma unroll
+          for (int i = 0; i < LP; ++i) {
+            if (i / NP != bd.level) continue;                              // uniform
+            const int H = p.lvl_h[i / NP], W = p.lvl_w[i / NP];
+            const float yf = floorf(py[i]), xf = floorf(px[i]);
+            const int y0 = static_cast<int>(yf), x0 = static_cast<int>(xf);
+            if (pw[i] == 0.f || y0 < bd.own0 || y0 > bd.own1) continue;
+            const float ly = py[i] - yf, lx = px[i] - xf;
+            // all four corner reads are issued unconditionally (clamped address, zero weight outside the image)
+            const int ya = max(y0, 0), yb = min(y0 + 1, H - 1), xa = max(x0, 0), xb = min(x0 + 1, W - 1);
+            const float wy0 = y0 >= 0 ? 1.f - ly : 0.f, wy1 = y0 + 1 < H ? ly : 0.f;
+            const float wx0 = x0 >= 0 ? 1.f - lx : 0.f, wx1 = x0 + 1 < W ? lx : 0.f;
+            const int ra = (ya - bd.row0) * W, rb = (yb - bd.row0) * W;
+            const U4 v00 = lds16(stage + (ra + xa) * 32), v01 = lds16(stage + (ra + xb) * 32);
+            const U4 v10 = lds16(stage + (rb + xa) * 32), v11 = lds16(stage + (rb + xb) * 32);
+            const float w00 = pw[i] * wy0 * wx0, w01 = pw[i] * wy0 * wx1, w10 = pw[i] * wy1 * wx0, w11 = pw[i] * wy1 * wx1;
+            const uint32_t u00[4] = {v00.x, v00.y, v00.z, v00.w}, u01[4] = {v01.x, v01.y, v01.z, v01.w};
+            const uint32_t u10[4] = {v10.x, v10.y, v10.z, v10.w}, u11[4] = {v11.x, v11.y, v11.z, v11.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float2 a = Cvt<T>::unpack(u00[j]), bq = Cvt<T>::unpack(u01[j]), c = Cvt<T>::unpack(u10[j]), d = Cvt<T>::unpack(u11[j]);
+              acc[2 * j] = fmaf(w00, a.x, fmaf(w01, bq.x, fmaf(w10, c.x, fmaf(w11, d.x, acc[2 * j]))));
+              acc[2 * j + 1] = fmaf(w00, a.y, fmaf(w01, bq.y, fmaf(w10, c.y, fmaf(w11, d.y, acc[2 * j + 1]))));
+            }
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[s]);
+      }
+      if (active) {
+        U4 o;
+        o.x = Cvt<T>::pack(acc[0], acc[1]);
+        o.y = Cvt<T>::pack(acc[2], acc[3]);
+        o.z = Cvt<T>::pack(acc[4], acc[5]);
+        o.w = Cvt<T>::pack(acc[6], acc[7]);
+        const long long row = static_cast<long long>(b) * p.nq + q;
+        *reinterpret_cast<U4*>(reinterpret_cast<T*>(p.out) + row * p.ld_out + m * MSDA_D + half * 8) = o;
+      }
+    }
+  }
+}
+
+int msda_plan(MsdaArgs* a) {
+  a->nbands = 0;
+  for (int l = 0; l < a->levels; ++l) {
+    const int H = a->lvl_h[l], W = a->lvl_w[l];
+    if (H < 1 || W < 1 || 2 * W > MS_STAGE_TOKENS) return -2;
+    const int rows_max = MS_STAGE_TOKENS / W;                    // rows a stage holds
+    if (H <= rows_max) {
+      if (a->nbands >= MSDA_MAX_BANDS) return -2;
+      a->bands[a->nbands++] = MsdaBand{l, 0, -1, H - 1, a->lvl_start[l], H * W * MSDA_D * 2};
+      continue;
+    }
+    const int own = rows_max - 1;                                // one halo row per band
+    for (int r0 = 0; r0 < H; r0 += own) {
+      if (a->nbands >= MSDA_MAX_BANDS) return -2;
+      const int r1 = std::min(r0 + own, H - 1);                  // last staged row (halo included)
+      const bool last = r0 + own >= H;
+      a->bands[a->nbands++] = MsdaBand{l, r0, r0 == 0 ? -1 : r0, last ? H - 1 : r0 + own - 1, a->lvl_start[l] + r0 * W, (r1 - r0 + 1) * W * MSDA_D * 2};
+    }
+  }
+  return 0;
+}
+
+template <typename T, int NL, int NP>
+static int launch_fwd(const MsdaArgs& a, cudaStream_t st) {
+  int e = ensure_max_dyn_smem(reinterpret_cast<const void*>(msda_fwd_kernel<T, NL, NP>), MS_SMEM);
+  if (e) return e;
+  const int items = a.batch * a.heads;
+  const unsigned grid = static_cast<unsigned>(std::min(items, current_device_sms()));
+  launch_k(msda_fwd_kernel<T, NL, NP>, dim3(grid), dim3(MS_THREADS), static_cast<size_t>(MS_SMEM), st, a);
+  return static_cast<int>(cudaGetLastError());
+}
+
+template <typename T>
+static int dispatch(const MsdaArgs& a, cudaStream_t st) {
+  if (a.levels == 1 && a.points == 2) return launch_fwd<T, 1, 2>(a, st);
+  if (a.levels == 2 && a.points == 4) return launch_fwd<T, 2, 4>(a, st);
+  if (a.levels == 1 && a.points == 4) return launch_fwd<T, 1, 4>(a, st);
+  if (a.levels == 2 && a.points == 2) return launch_fwd<T, 2, 2>(a, st);
+  if (a.levels == 4 && a.points == 4) return launch_fwd<T, 4, 4>(a, st);
+  return -2;
+}
+
+int msda_launch(int dtype, const MsdaArgs& a, cudaStream_t st) {
+  if (a.nbands < 1 || a.batch < 1 || a.nq < 1) return -2;
+  return dtype == DT_BF16 ? dispatch<__nv_bfloat16>(a, st) : dispatch<__half>(a, st);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Operator boundary: ms_deform_attn_forward(value, spatial_shapes, level_start_index, sampling_loc, attn_weight)
+// (ms_deform_attn.h:19-35 -> ms_deform_attn_cuda.cu:20-80 -> cuh:237-299).  Same arithmetic and the same operation
+// order as the reference's bilinear (cuh:33-84): val = w1 v1 + w2 v2 + w3 v3 + w4 v4; col += val * attn_weight.
+template <typename T> struct Elt;
+template <> struct Elt<float> {
+  static constexpr int VEC = 4;
+  static __device__ __forceinline__ float ld(const float* p) { return __ldg(p); }
+  static __device__ __forceinline__ void unpack(const U4& u, float (&f)[4]) {
+    f[0] = __uint_as_float(u.x); f[1] = __uint_as_float(u.y); f[2] = __uint_as_float(u.z); f[3] = __uint_as_float(u.w);
+  }
+  static __device__ __forceinline__ void store(float* p, const float (&f)[4]) { *reinterpret_cast<float4*>(p) = make_float4(f[0], f[1], f[2], f[3]); }
+};
+template <> struct Elt<__half> {
+  static constexpr int VEC = 8;
+  static __device__ __forceinline__ float ld(const __half* p) { return __half2float(__ldg(p)); }
+  static __device__ __forceinline__ void unpack(const U4& u, float (&f)[8]) {
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { const float2 t = Cvt<__half>::unpack(w[j]); f[2 * j] = t.x; f[2 * j + 1] = t.y; }
+  }
+  static __device__ __forceinline__ void store(__half* p, const float (&f)[8]) {
+    U4 o; o.x = Cvt<__half>::pack(f[0], f[1]); o.y = Cvt<__half>::pack(f[2], f[3]); o.z = Cvt<__half>::pack(f[4], f[5]); o.w = Cvt<__half>::pack(f[6], f[7]);
+    *reinterpret_cast<U4*>(p) = o;
+  }
+};
+template <> struct Elt<__nv_bfloat16> {
+  static constexpr int VEC = 8;
+  static __device__ __forceinline__ float ld(const __nv_bfloat16* p) { return __bfloat162float(__ldg(p)); }
+  static __device__ __forceinline__ void unpack(const U4& u, float (&f)[8]) {
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { const float2 t = Cvt<__nv_bfloat16>::unpack(w[j]); f[2 * j] = t.x; f[2 * j + 1] = t.y; }
+  }
+  static __device__ __forceinline__ void store(__nv_bfloat16* p, const float (&f)[8]) {
+    U4 o; o.x = Cvt<__nv_bfloat16>::pack(f[0], f[1]); o.y = Cvt<__nv_bfloat16>::pack(f[2], f[3]); o.z = Cvt<__nv_bfloat16>::pack(f[4], f[5]); o.w = Cvt<__nv_bfloat16>::pack(f[6], f[7]);
+    *reinterpret_cast<U4*>(p) = o;
+  }
+};
 
 __device__ __forceinline__ U4 ldg_nc16(const void* p) {
   U4 r;
@@ -22,106 +291,184 @@ __device__ __forceinline__ U4 ldg_nc16(const void* p) {
   return r;
 }
 
-template <typename T, int NL, int NP>   // levels, points per head and level
-__global__ void __launch_bounds__(256, (NL * NP <= 2) ? 8 : ((NL * NP <= 4) ? 6 : 4)) msda_fwd_kernel(const MsdaArgs p) {
-  pdl_sync();   // programmatic dependent launch: release the successor, wait for the predecessor (launch.h)
-  constexpr int D = 16;
-  constexpr int LP = NL * NP;
+template <typename T>
+__global__ void __launch_bounds__(256) msda_op_kernel(const MsdaOpArgs p) {
+  pdl_sync();
+  constexpr int VEC = Elt<T>::VEC;
+  const int groups = p.D / VEC;
   const long long gid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  const int half = static_cast<int>(gid & 1);
-  const long long hm = gid >> 1;
-  const int m = static_cast<int>(hm % p.heads);
-  const long long row = hm / p.heads;                 // b * nq + q
-  if (row >= static_cast<long long>(p.batch) * p.nq) return;
-  const int b = static_cast<int>(row / p.nq);
-
-  // ---- per-(query, head) scalars: 2*LP offsets, LP logits (16-bit), reference box (fp32)
-  const T* oa = reinterpret_cast<const T*>(p.offs_logits) + row * p.ld_ol;
-  float off[2 * LP], w[LP];
-  {
-    const uint32_t* o32 = reinterpret_cast<const uint32_t*>(oa + m * (2 * LP));
+  const int g = static_cast<int>(gid % groups);
+  const long long qm = gid / groups;                      // (b*Lq + q)*M + m
+  if (qm >= static_cast<long long>(p.B) * p.Lq * p.M) return;
+  const int m = static_cast<int>(qm % p.M);
+  const long long bq = qm / p.M;
+  const int b = static_cast<int>(bq / p.Lq);
+  const int LP = p.L * p.P;
+  const T* loc = reinterpret_cast<const T*>(p.sampling_loc) + qm * LP * 2;
+  const T* aw = reinterpret_cast<const T*>(p.attn_weight) + qm * LP;
+  const long long row_stride = static_cast<long long>(p.M) * p.D;            // elements between tokens
+  const T* vb = reinterpret_cast<const T*>(p.value) + static_cast<long long>(b) * p.S * row_stride + m * p.D + g * VEC;
+  float col[VEC];
 #pragma unroll
-    for (int i = 0; i < LP; ++i) {
-      const float2 f = Cvt<T>::unpack(__ldg(o32 + i));
-      off[2 * i] = f.x;
-      off[2 * i + 1] = f.y;
-    }
-    const T* lg = oa + p.heads * (2 * LP) + m * LP;
-    float mx = -INFINITY;
+  for (int j = 0; j < VEC; ++j) col[j] = 0.f;
+  for (int l = 0; l < p.L; ++l) {
+    const int H = static_cast<int>(__ldg(p.spatial_shapes + 2 * l)), W = static_cast<int>(__ldg(p.spatial_shapes + 2 * l + 1));
+    const T* vl = vb + __ldg(p.level_start_index + l) * row_stride;
+    for (int pt = 0; pt < p.P; ++pt) {
+      const int i = l * p.P + pt;
+      const float w_im = Elt<T>::ld(loc + 2 * i) * W - 0.5f, h_im = Elt<T>::ld(loc + 2 * i + 1) * H - 0.5f;   // cuh:285-286
+      const float weight = Elt<T>::ld(aw + i);
+      if (!(h_im > -1.f && w_im > -1.f && h_im < H && w_im < W)) continue;                                     // cuh:288
+      const float hf = floorf(h_im), wf = floorf(w_im);
+      const int h_low = static_cast<int>(hf), w_low = static_cast<int>(wf), h_high = h_low + 1, w_high = w_low + 1;
+      const float lh = h_im - hf, lw = w_im - wf, hh = 1.f - lh, hw = 1.f - lw;
+      const bool t = h_low >= 0, bt = h_high <= H - 1, lf = w_low >= 0, rt = w_high <= W - 1;
+      const U4 zero{0u, 0u, 0u, 0u};
+      // issue every corner load first (clamped addresses are always in range), then combine as cuh:58-84
+      const int hc0 = max(h_low, 0), hc1 = min(h_high, H - 1), wc0 = max(w_low, 0), wc1 = min(w_high, W - 1);
+      const U4 r1 = ldg_nc16(vl + (static_cast<long long>(hc0) * W + wc0) * row_stride);
+      const U4 r2 = ldg_nc16(vl + (static_cast<long long>(hc0) * W + wc1) * row_stride);
+      const U4 r3 = ldg_nc16(vl + (static_cast<long long>(hc1) * W + wc0) * row_stride);
+      const U4 r4 = ldg_nc16(vl + (static_cast<long long>(hc1) * W + wc1) * row_stride);
+      float v1[VEC], v2[VEC], v3[VEC], v4[VEC];
+      Elt<T>::unpack((t && lf) ? r1 : zero, v1);
+      Elt<T>::unpack((t && rt) ? r2 : zero, v2);
+      Elt<T>::unpack((bt && lf) ? r3 : zero, v3);
+      Elt<T>::unpack((bt && rt) ? r4 : zero, v4);
+      const float w1 = hh * hw, w2 = hh * lw, w3 = lh * hw, w4 = lh * lw;
 #pragma unroll
-    for (int i = 0; i < LP; ++i) {
-      w[i] = Cvt<T>::to_f(lg[i]);
-      mx = fmaxf(mx, w[i]);
-    }
-    float sum = 0.f;
-#pragma unroll
-    for (int i = 0; i < LP; ++i) {
-      w[i] = __expf(w[i] - mx);
-      sum += w[i];
-    }
-    const float inv = 1.f / sum;
-#pragma unroll
-    for (int i = 0; i < LP; ++i) w[i] *= inv;
-  }
-  const float4 ref = __ldg(reinterpret_cast<const float4*>(p.ref) + row);
-  const float sx = ref.z * (0.5f / NP);
-  const float sy = ref.w * (0.5f / NP);
-
-  const T* vbase = reinterpret_cast<const T*>(p.value) + static_cast<long long>(b) * p.S * p.ldv + m * D + half * 8;
-  float acc[8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
-
-#pragma unroll
-  for (int i = 0; i < LP; ++i) {
-    const int l = i / NP;
-    const int H = p.lvl_h[l], W = p.lvl_w[l];
-    const float x = (ref.x + off[2 * i] * sx) * W - 0.5f;      // ms_deform_attn.py:125-127, cuh:285-286
-    const float y = (ref.y + off[2 * i + 1] * sy) * H - 0.5f;
-    if (!(y > -1.f && x > -1.f && y < H && x < W)) continue;   // cuh:288
-    const float xf = floorf(x), yf = floorf(y);
-    const int x0 = static_cast<int>(xf), y0 = static_cast<int>(yf);
-    const float lx = x - xf, ly = y - yf;
-    const T* vl = vbase + static_cast<long long>(p.lvl_start[l]) * p.ldv;
-    const float wi = w[i];
-#pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      const int xi = x0 + (c & 1), yi = y0 + (c >> 1);
-      if (xi < 0 || yi < 0 || xi >= W || yi >= H) continue;
-      const float cw = wi * ((c & 1) ? lx : 1.f - lx) * ((c >> 1) ? ly : 1.f - ly);
-      const U4 v = ldg_nc16(vl + static_cast<long long>(yi * W + xi) * p.ldv);
-      const uint32_t u[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float2 f = Cvt<T>::unpack(u[j]);
-        acc[2 * j] = fmaf(cw, f.x, acc[2 * j]);
-        acc[2 * j + 1] = fmaf(cw, f.y, acc[2 * j + 1]);
-      }
+      for (int j = 0; j < VEC; ++j) col[j] += (w1 * v1[j] + w2 * v2[j] + w3 * v3[j] + w4 * v4[j]) * weight;
     }
   }
-  U4 o;
-  o.x = Cvt<T>::pack(acc[0], acc[1]);
-  o.y = Cvt<T>::pack(acc[2], acc[3]);
-  o.z = Cvt<T>::pack(acc[4], acc[5]);
-  o.w = Cvt<T>::pack(acc[6], acc[7]);
-  *reinterpret_cast<U4*>(reinterpret_cast<T*>(p.out) + row * p.ld_out + m * D + half * 8) = o;
+  Elt<T>::store(reinterpret_cast<T*>(p.out) + qm * p.D + g * VEC, col);
+}
+
+// Any head dim (models/ops/test.py runs D = 2 and odd channel counts): one thread per output channel, scalar loads.
+template <typename T>
+__global__ void __launch_bounds__(256) msda_op_scalar_kernel(const MsdaOpArgs p) {
+  pdl_sync();
+  const long long gid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int c = static_cast<int>(gid % p.D);
+  const long long qm = gid / p.D;
+  if (qm >= static_cast<long long>(p.B) * p.Lq * p.M) return;
+  const int m = static_cast<int>(qm % p.M);
+  const int b = static_cast<int>(qm / p.M / p.Lq);
+  const int LP = p.L * p.P;
+  const T* loc = reinterpret_cast<const T*>(p.sampling_loc) + qm * LP * 2;
+  const T* aw = reinterpret_cast<const T*>(p.attn_weight) + qm * LP;
+  const long long row_stride = static_cast<long long>(p.M) * p.D;
+  const T* vb = reinterpret_cast<const T*>(p.value) + static_cast<long long>(b) * p.S * row_stride + m * p.D + c;
+  float col = 0.f;
+  for (int l = 0; l < p.L; ++l) {
+    const int H = static_cast<int>(__ldg(p.spatial_shapes + 2 * l)), W = static_cast<int>(__ldg(p.spatial_shapes + 2 * l + 1));
+    const T* vl = vb + __ldg(p.level_start_index + l) * row_stride;
+    for (int pt = 0; pt < p.P; ++pt) {
+      const int i = l * p.P + pt;
+      const float w_im = Elt<T>::ld(loc + 2 * i) * W - 0.5f, h_im = Elt<T>::ld(loc + 2 * i + 1) * H - 0.5f;
+      const float weight = Elt<T>::ld(aw + i);
+      if (!(h_im > -1.f && w_im > -1.f && h_im < H && w_im < W)) continue;
+      const float hf = floorf(h_im), wf = floorf(w_im);
+      const int h_low = static_cast<int>(hf), w_low = static_cast<int>(wf), h_high = h_low + 1, w_high = w_low + 1;
+      const float lh = h_im - hf, lw = w_im - wf, hh = 1.f - lh, hw = 1.f - lw;
+      const float v1 = (h_low >= 0 && w_low >= 0) ? Elt<T>::ld(vl + (static_cast<long long>(h_low) * W + w_low) * row_stride) : 0.f;
+      const float v2 = (h_low >= 0 && w_high <= W - 1) ? Elt<T>::ld(vl + (static_cast<long long>(h_low) * W + w_high) * row_stride) : 0.f;
+      const float v3 = (h_high <= H - 1 && w_low >= 0) ? Elt<T>::ld(vl + (static_cast<long long>(h_high) * W + w_low) * row_stride) : 0.f;
+      const float v4 = (h_high <= H - 1 && w_high <= W - 1) ? Elt<T>::ld(vl + (static_cast<long long>(h_high) * W + w_high) * row_stride) : 0.f;
+      col += (hh * hw * v1 + hh * lw * v2 + lh * hw * v3 + lh * lw * v4) * weight;
+    }
+  }
+  T* o = reinterpret_cast<T*>(p.out) + qm * p.D + c;
+  if constexpr (sizeof(T) == 4) *o = col;
+  else *o = Cvt<T>::from_f(col);
 }
 
 template <typename T>
-static int dispatch(const MsdaArgs& a, cudaStream_t st) {
-  const long long threads = static_cast<long long>(a.batch) * a.nq * a.heads * 2;
+static int launch_op(const MsdaOpArgs& a, cudaStream_t st) {
+  if (a.D % Elt<T>::VEC != 0 || (reinterpret_cast<uintptr_t>(a.value) & 15) || (reinterpret_cast<uintptr_t>(a.out) & 15)) {
+    const long long threads = static_cast<long long>(a.B) * a.Lq * a.M * a.D;
+    launch_k(msda_op_scalar_kernel<T>, dim3(static_cast<unsigned>((threads + 255) / 256)), dim3(256), 0, st, a);
+    return static_cast<int>(cudaGetLastError());
+  }
+  const long long threads = static_cast<long long>(a.B) * a.Lq * a.M * (a.D / Elt<T>::VEC);
   const unsigned grid = static_cast<unsigned>((threads + 255) / 256);
-  if (a.levels == 1 && a.points == 2) launch_k(msda_fwd_kernel<T, 1, 2>, dim3(grid), dim3(256), 0, st, a);
-  else if (a.levels == 2 && a.points == 4) launch_k(msda_fwd_kernel<T, 2, 4>, dim3(grid), dim3(256), 0, st, a);
-  else if (a.levels == 1 && a.points == 4) launch_k(msda_fwd_kernel<T, 1, 4>, dim3(grid), dim3(256), 0, st, a);
-  else if (a.levels == 2 && a.points == 2) launch_k(msda_fwd_kernel<T, 2, 2>, dim3(grid), dim3(256), 0, st, a);
-  else if (a.levels == 4 && a.points == 4) launch_k(msda_fwd_kernel<T, 4, 4>, dim3(grid), dim3(256), 0, st, a);
-  else return -2;
+  launch_k(msda_op_kernel<T>, dim3(grid), dim3(256), 0, st, a);
   return static_cast<int>(cudaGetLastError());
 }
 
-int msda_launch(int dtype, const MsdaArgs& a, cudaStream_t st) {
-  return dtype == DT_BF16 ? dispatch<__nv_bfloat16>(a, st) : dispatch<__half>(a, st);
+// Backward of the operator (ms_deform_attn.h:37-60 -> ms_deform_attn_cuda.cu:83-154 -> cuh:301-920), fp32.
+// The reference needs six kernel variants because it spends one thread per channel and must reduce the sampling-location
+// and attention-weight gradients across the channels of a (query, head, level, point) through shared memory.  Here one
+// thread owns a whole (query, head): it walks the D channels of every sample itself, so those two gradients are plain
+// register sums (written once, no atomics, no block reduction); only grad_value, which many queries scatter into, uses
+// atomicAdd - as in the reference (cuh:130-152).
+__global__ void __launch_bounds__(128) msda_op_backward_kernel(const MsdaOpArgs p, const float* __restrict__ grad_out,
+                                                               float* __restrict__ grad_value, float* __restrict__ grad_loc,
+                                                               float* __restrict__ grad_aw) {
+  const long long qm = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;        // (b*Lq + q)*M + m
+  if (qm >= static_cast<long long>(p.B) * p.Lq * p.M) return;
+  const int m = static_cast<int>(qm % p.M);
+  const int b = static_cast<int>(qm / p.M / p.Lq);
+  const int LP = p.L * p.P, D = p.D;
+  const float* loc = reinterpret_cast<const float*>(p.sampling_loc) + qm * LP * 2;
+  const float* aw = reinterpret_cast<const float*>(p.attn_weight) + qm * LP;
+  const long long row_stride = static_cast<long long>(p.M) * D;
+  const long long voff = static_cast<long long>(b) * p.S * row_stride + m * D;
+  const float* vb = reinterpret_cast<const float*>(p.value) + voff;
+  float* gvb = grad_value + voff;
+  const float* go = grad_out + qm * D;
+  for (int l = 0; l < p.L; ++l) {
+    const int H = static_cast<int>(__ldg(p.spatial_shapes + 2 * l)), W = static_cast<int>(__ldg(p.spatial_shapes + 2 * l + 1));
+    const long long lvl = __ldg(p.level_start_index + l) * row_stride;
+    for (int pt = 0; pt < p.P; ++pt) {
+      const int i = l * p.P + pt;
+      const float w_im = __ldg(loc + 2 * i) * W - 0.5f, h_im = __ldg(loc + 2 * i + 1) * H - 0.5f;
+      const float weight = __ldg(aw + i);
+      float g_w = 0.f, g_h = 0.f, g_a = 0.f;
+      if (h_im > -1.f && w_im > -1.f && h_im < H && w_im < W) {
+        const float hf = floorf(h_im), wf = floorf(w_im);
+        const int h_low = static_cast<int>(hf), w_low = static_cast<int>(wf), h_high = h_low + 1, w_high = w_low + 1;
+        const float lh = h_im - hf, lw = w_im - wf, hh = 1.f - lh, hw = 1.f - lw;
+        const bool ok1 = h_low >= 0 && w_low >= 0, ok2 = h_low >= 0 && w_high <= W - 1;
+        const bool ok3 = h_high <= H - 1 && w_low >= 0, ok4 = h_high <= H - 1 && w_high <= W - 1;
+        const long long o1 = lvl + (static_cast<long long>(h_low) * W + w_low) * row_stride, o2 = o1 + row_stride;
+        const long long o3 = o1 + static_cast<long long>(W) * row_stride, o4 = o3 + row_stride;
+        const float w1 = hh * hw, w2 = hh * lw, w3 = lh * hw, w4 = lh * lw;
+        for (int c = 0; c < D; ++c) {
+          const float top = __ldg(go + c), tv = top * weight;
+          const float v1 = ok1 ? __ldg(vb + o1 + c) : 0.f, v2 = ok2 ? __ldg(vb + o2 + c) : 0.f;
+          const float v3 = ok3 ? __ldg(vb + o3 + c) : 0.f, v4 = ok4 ? __ldg(vb + o4 + c) : 0.f;
+          // d(bilinear)/dh and /dw (cuh:112-152)
+          const float dh = -hw * v1 - lw * v2 + hw * v3 + lw * v4;
+          const float dw = -hh * v1 + hh * v2 - lh * v3 + lh * v4;
+          g_h += dh * tv;
+          g_w += dw * tv;
+          g_a += top * (w1 * v1 + w2 * v2 + w3 * v3 + w4 * v4);
+          if (ok1) atomicAdd(gvb + o1 + c, w1 * tv);
+          if (ok2) atomicAdd(gvb + o2 + c, w2 * tv);
+          if (ok3) atomicAdd(gvb + o3 + c, w3 * tv);
+          if (ok4) atomicAdd(gvb + o4 + c, w4 * tv);
+        }
+      }
+      grad_loc[(qm * LP + i) * 2] = W * g_w;         // cuh:156-158: d/d(normalised x) = width * d/dw_im
+      grad_loc[(qm * LP + i) * 2 + 1] = H * g_h;
+      grad_aw[qm * LP + i] = g_a;
+    }
+  }
+}
+
+int msda_op_backward_launch(const MsdaOpArgs& a, const float* grad_out, float* grad_value, float* grad_loc, float* grad_aw, cudaStream_t st) {
+  cudaError_t e = cudaMemsetAsync(grad_value, 0, static_cast<size_t>(a.B) * a.S * a.M * a.D * sizeof(float), st);   // at::zeros_like, ms_deform_attn_cuda.cu:120
+  if (e != cudaSuccess) return static_cast<int>(e);
+  const long long threads = static_cast<long long>(a.B) * a.Lq * a.M;
+  msda_op_backward_kernel<<<static_cast<unsigned>((threads + 127) / 128), 128, 0, st>>>(a, grad_out, grad_value, grad_loc, grad_aw);
+  return static_cast<int>(cudaGetLastError());
+}
+
+int msda_op_launch(int etype, const MsdaOpArgs& a, cudaStream_t st) {
+  if (etype == MSDA_ET_F32) return launch_op<float>(a, st);
+  if (etype == MSDA_ET_F16) return launch_op<__half>(a, st);
+  if (etype == MSDA_ET_BF16) return launch_op<__nv_bfloat16>(a, st);
+  return -2;
 }
 
 }  // namespace lwb

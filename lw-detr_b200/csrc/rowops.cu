@@ -291,12 +291,7 @@ int topk_launch(const float* score, int B, int S, int k, int* idx_out, cudaStrea
   while (np2 < S) np2 <<= 1;
   if (np2 > 16384 || k > S) return -2;
   const size_t smem = static_cast<size_t>(np2) * 8;
-  static bool attr = false;
-  if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * 8);
-    if (e != cudaSuccess) return static_cast<int>(e);
-    attr = true;
-  }
+  if (int e = ensure_max_dyn_smem(reinterpret_cast<const void*>(topk_kernel), 16384 * 8)) return e;
   launch_k(topk_kernel, dim3(B), dim3(1024), smem, st, score, S, np2, k, idx_out);
   return static_cast<int>(cudaGetLastError());
 }
@@ -461,13 +456,8 @@ int postprocess_launch(const float* logits, const float* boxes, const float* tar
   int np2m = 1;
   while (np2m < ncand) np2m <<= 1;
   if (k > part_len || np2m > 16384 || B < 1) return -2;
-  static bool attr = false;
-  if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(postprocess_part_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * 8);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(postprocess_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * 8);
-    if (e != cudaSuccess) return static_cast<int>(e);
-    attr = true;
-  }
+  if (int e = ensure_max_dyn_smem(reinterpret_cast<const void*>(postprocess_part_kernel), 16384 * 8)) return e;
+  if (int e = ensure_max_dyn_smem(reinterpret_cast<const void*>(postprocess_merge_kernel), 16384 * 8)) return e;
   launch_k(postprocess_part_kernel, dim3(B * parts), dim3(1024), static_cast<size_t>(np2) * 8, st, logits, S, parts, part_len, np2, k, work);
   launch_k(postprocess_merge_kernel, dim3(B), dim3(1024), static_cast<size_t>(np2m) * 8, st, logits, boxes, target_sizes,
            static_cast<const int*>(work), S, ncand, np2m, ncls, k, scores, labels, out_boxes);

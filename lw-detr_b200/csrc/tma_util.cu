@@ -5,6 +5,10 @@
 #include <cuda_runtime.h>
 
 #include <cstdio>
+#include <map>
+#include <mutex>
+#include <set>
+#include <utility>
 
 #include "gemm_tc.h"
 
@@ -12,6 +16,34 @@ namespace lwb {
 
 int& pdl_enabled() {
   static int v = 1;
+  return v;
+}
+
+int ensure_max_dyn_smem(const void* kernel, int bytes) {
+  static std::mutex mu;
+  static std::set<std::pair<const void*, int>> done;
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return static_cast<int>(e);
+  std::lock_guard<std::mutex> lk(mu);
+  if (done.count({kernel, dev})) return 0;
+  e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e != cudaSuccess) return static_cast<int>(e);
+  done.insert({kernel, dev});
+  return 0;
+}
+
+int current_device_sms() {
+  static std::mutex mu;
+  static std::map<int, int> sms;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+  std::lock_guard<std::mutex> lk(mu);
+  auto it = sms.find(dev);
+  if (it != sms.end()) return it->second;
+  int v = 0;
+  if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = 148;
+  sms[dev] = v;
   return v;
 }
 

@@ -14,6 +14,15 @@ def _tol(dt):
     return 3e-3 if dt == torch.float16 else 2e-2
 
 
+def _rel_l2(a, b):
+    return ((a - b).norm() / (b.norm() + 1e-30)).item()
+
+
+# rel-L2 bounds next to the max-abs ones (a single wrong low-magnitude row passes a max-abs / max|ref| test):
+# 16-bit rounding of P and of the output gives ~3e-4 (fp16) / ~2.5e-3 (bf16) on these shapes
+REL_L2 = {torch.float16: 1e-3, torch.bfloat16: 8e-3}
+
+
 @pytest.mark.parametrize("dt", DTYPES)
 @pytest.mark.parametrize("nseq,seqlen,heads,dh", [(32, 100, 12, 16), (2, 1600, 12, 16), (16, 100, 12, 32), (1, 1600, 12, 32),
                                                   (16, 100, 12, 64), (1, 1600, 12, 64), (3, 300, 8, 32), (2, 100, 8, 32),
@@ -33,6 +42,10 @@ def test_attention_matches_softmax_reference(dt, nseq, seqlen, heads, dh):
     ref = ref.transpose(1, 2).reshape(nseq * seqlen, C)
     err = (out.float() - ref).abs().max().item()
     assert err <= _tol(dt) * ref.abs().max().item(), err
+    assert _rel_l2(out.float(), ref) <= REL_L2[dt]
+    # per-row bound: no query row may be off by more than a few 16-bit ulps of its own magnitude
+    row_err = (out.float() - ref).norm(dim=1) / (ref.norm(dim=1) + 1e-6)
+    assert row_err.max().item() <= 4 * REL_L2[dt], row_err.max().item()
 
 
 @pytest.mark.parametrize("dt", DTYPES)
@@ -58,6 +71,7 @@ def test_attention_late_dominant_keys(dt, dh):
     assert torch.isfinite(out.float()).all()
     err = (out.float() - ref).abs().max().item()
     assert err <= _tol(dt) * ref.abs().max().item(), err
+    assert _rel_l2(out.float(), ref) <= REL_L2[dt]
 
 
 @pytest.mark.parametrize("dt", DTYPES)
@@ -73,6 +87,7 @@ def test_layernorm(dt, rows, C, eps):
     capi.layernorm(x, y, w, b, eps)
     ref = F.layer_norm(x.float(), (C,), w, b, eps)
     assert (y.float() - ref).abs().max().item() <= _tol(dt) * ref.abs().max().item()
+    assert _rel_l2(y.float(), ref) <= (5e-4 if dt == torch.float16 else 4e-3)
 
 
 @pytest.mark.parametrize("dt", DTYPES)
@@ -94,7 +109,9 @@ def test_msda_forward_matches_oracle(dt, B, Lq, M, L, P, shapes):
     ref_box = torch.rand(B * Lq, 4, generator=g) * torch.tensor([1.2, 1.2, 0.6, 0.6]) - torch.tensor([0.1, 0.1, 0.0, 0.0])
     out = torch.full((B * Lq, d), float("nan"), dtype=dt, device="cuda")
     vg = value_all.cuda()
-    capi.msda_forward(vg.reshape(B * S, nlayers * d)[:, d:2 * d], ol.cuda(), ref_box.cuda(), out, B, S, Lq, M, L, P, shapes)
+    # the engine's layout: all layers' values head-major in one buffer [B][layer][M][S][16]; use the middle layer's slice
+    hm = vg.reshape(B, S, nlayers, M, 16).permute(0, 2, 3, 1, 4).contiguous()
+    capi.msda_forward(hm[:, 1], ol.cuda(), ref_box.cuda(), out, B, S, Lq, M, L, P, shapes, v_image_stride=nlayers * M * S * 16)
     # oracle on the same rounded inputs (ops/modules/ms_deform_attn.py:118-131 + msda core)
     value = value_all[..., d:2 * d].float().reshape(B, S, M, D)
     off = ol[:, :M * L * P * 2].float().reshape(B, Lq, M, L, P, 2)
@@ -104,6 +121,83 @@ def test_msda_forward_matches_oracle(dt, B, Lq, M, L, P, shapes):
     ref = orc.msda_core(value, shapes, loc, aw).reshape(B * Lq, d)
     err = (out.float().cpu() - ref).abs().max().item()
     assert err <= _tol(dt) * max(ref.abs().max().item(), 1.0), err
+    assert _rel_l2(out.float().cpu(), ref) <= (1e-3 if dt == torch.float16 else 8e-3)
+
+
+@pytest.mark.parametrize("dt", DTYPES)
+def test_msda_forward_valid_ratios(dt):
+    """Padded batches scale the reference boxes per level by the valid ratios (transformer.py:352-353)."""
+    from b200 import capi
+    from oracle import lwdetr_oracle as orc
+    B, Lq, M, L, P, shapes = 2, 300, 24, 2, 4, [(80, 80), (20, 20)]
+    g = torch.Generator().manual_seed(11)
+    d, S = M * 16, sum(h * w for h, w in shapes)
+    value = torch.randn(B, S, d, generator=g).to(dt)
+    ol = torch.cat([torch.randn(B * Lq, M * L * P * 2, generator=g) * 2.0, torch.randn(B * Lq, M * L * P, generator=g)], 1).to(dt)
+    ref_box = torch.rand(B * Lq, 4, generator=g) * torch.tensor([1.0, 1.0, 0.5, 0.5])
+    vr = torch.tensor([[[1.0, 1.0], [1.0, 1.0]], [[0.8, 0.65], [0.8, 0.7]]])
+    out = torch.full((B * Lq, d), float("nan"), dtype=dt, device="cuda")
+    capi.msda_forward(capi.value_to_head_major(value.cuda().reshape(B * S, d), B, S, M), ol.cuda(), ref_box.cuda(), out, B, S, Lq, M, L, P, shapes,
+                      valid_ratio=vr.cuda().contiguous())
+    off = ol[:, :M * L * P * 2].float().reshape(B, Lq, M, L, P, 2)
+    aw = ol[:, M * L * P * 2:].float().reshape(B, Lq, M, L * P).softmax(-1).reshape(B, Lq, M, L, P)
+    rb = ref_box.reshape(B, Lq, 1, 4) * torch.cat([vr, vr], -1)[:, None]                     # [B, Lq, L, 4]
+    loc = rb[:, :, None, :, None, :2] + off / P * rb[:, :, None, :, None, 2:] * 0.5
+    ref = orc.msda_core(value.float().reshape(B, S, M, 16), shapes, loc, aw).reshape(B * Lq, d)
+    assert (out.float().cpu() - ref).abs().max().item() <= _tol(dt) * max(ref.abs().max().item(), 1.0)
+
+
+def _op_inputs(N, S, M, D, Lq, L, P, dt, seed=3):
+    """models/ops/test.py:37-41 recipe."""
+    torch.manual_seed(seed)
+    value = (torch.rand(N, S, M, D).cuda() * 0.01).to(dt)
+    loc = torch.rand(N, Lq, M, L, P, 2).cuda().to(dt)
+    aw = torch.rand(N, Lq, M, L, P).cuda() + 1e-5
+    aw = (aw / aw.sum(-1, keepdim=True).sum(-2, keepdim=True)).to(dt)
+    return value, loc, aw
+
+
+@pytest.mark.parametrize("dt", [torch.float32, torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("N,M,D,Lq,L,P,shapes", [(1, 2, 2, 2, 2, 2, [(6, 4), (3, 2)]),             # models/ops/test.py:27-31
+                                                 (2, 2, 30, 2, 2, 2, [(6, 4), (3, 2)]),            # channel counts of test.py:111
+                                                 (2, 2, 32, 2, 2, 2, [(6, 4), (3, 2)]),
+                                                 (1, 2, 71, 2, 2, 2, [(6, 4), (3, 2)]),
+                                                 (2, 16, 16, 300, 1, 2, [(40, 40)]),               # small / medium decoder shapes
+                                                 (2, 24, 16, 300, 2, 4, [(80, 80), (20, 20)]),      # large / xlarge
+                                                 (2, 8, 32, 100, 4, 4, [(32, 32), (16, 16), (8, 8), (4, 4)])])   # Deformable-DETR default
+def test_ms_deform_attn_forward_operator(dt, N, M, D, Lq, L, P, shapes):
+    """The reference operator's interface (ms_deform_attn.h:19-35) replayed with models/ops/test.py's recipe against the
+    reference's own checker ms_deform_attn_core_pytorch (= oracle msda_core, pinned to the grid_sample form on CPU)."""
+    from b200 import capi
+    from oracle import lwdetr_oracle as orc
+    sh = torch.as_tensor(shapes, dtype=torch.long).cuda()
+    lsi = torch.cat((sh.new_zeros((1,)), sh.prod(1).cumsum(0)[:-1]))
+    S = int(sh.prod(1).sum())
+    value, loc, aw = _op_inputs(N, S, M, D, Lq, L, P, dt)
+    out = capi.ms_deform_attn_forward(value, sh, lsi, loc, aw, im2col_step=2 if N <= 2 else 64)
+    assert out.shape == (N, Lq, M * D) and out.dtype == dt
+    ref = orc.msda_core(value.double().cpu(), shapes, loc.double().cpu(), aw.double().cpu())
+    if dt == torch.float32:
+        assert torch.allclose(out.cpu().double(), ref, rtol=1e-2, atol=1e-3)         # the reference's own float criterion (test.py:82)
+        assert (out.cpu().double() - ref).abs().max().item() <= 2e-8 + 1e-5 * ref.abs().max().item()
+    else:
+        assert (out.cpu().double() - ref).abs().max().item() <= _tol(dt) * ref.abs().max().item()
+
+
+def test_ms_deform_attn_forward_error_behaviour():
+    """Same failures as the reference op: CPU tensors, non-contiguous tensors, batch not divisible by im2col_step."""
+    from b200 import capi
+    sh = torch.as_tensor([(6, 4), (3, 2)], dtype=torch.long).cuda()
+    lsi = torch.cat((sh.new_zeros((1,)), sh.prod(1).cumsum(0)[:-1]))
+    value, loc, aw = _op_inputs(3, 30, 2, 16, 2, 2, 2, torch.float32)
+    with pytest.raises(RuntimeError, match="CPU"):
+        capi.ms_deform_attn_forward(value.cpu(), sh, lsi, loc, aw)
+    with pytest.raises(RuntimeError, match="contiguous"):
+        capi.ms_deform_attn_forward(value.transpose(1, 2), sh, lsi, loc, aw)
+    with pytest.raises(RuntimeError, match="im2col_step"):
+        capi.ms_deform_attn_forward(value, sh, lsi, loc, aw, im2col_step=2)        # 3 % 2 != 0  (ms_deform_attn_cuda.cu:50-52)
+    out = capi.ms_deform_attn_forward(value, sh, lsi, loc, aw, im2col_step=64)     # min(B, step) = 3 divides 3
+    assert torch.isfinite(out).all()
 
 
 @pytest.mark.parametrize("B,S,k", [(2, 1600, 300), (3, 6800, 300), (1, 1600, 100), (2, 50, 50)])
@@ -194,3 +288,95 @@ def test_postprocess_matches_reference_golden(name):
     gap = torch.minimum((rs - torch.roll(rs, 1, 1)).abs(), (rs - torch.roll(rs, -1, 1)).abs())
     assert (same | (gap < 1e-6)).all() and same.float().mean() > 0.98
     assert torch.allclose(xyxy[same], rb[same], rtol=1e-6, atol=1e-3)
+
+
+def _autograd_reference(value, shapes, loc, aw, grad_out):
+    """Gradients of the oracle's msda_core (pinned to the grid_sample form / the reference's ms_deform_attn_core_pytorch)
+    by torch autograd in float64 on the CPU."""
+    from oracle import lwdetr_oracle as orc
+    v, l, a = [t.detach().double().cpu().requires_grad_(True) for t in (value, loc, aw)]
+    out = orc.msda_core(v, shapes, l, a)
+    out.backward(grad_out.double().cpu())
+    return out.detach(), v.grad, l.grad, a.grad
+
+
+@pytest.mark.parametrize("N,M,D,Lq,L,P,shapes", [(1, 2, 2, 2, 2, 2, [(6, 4), (3, 2)]),            # models/ops/test.py:27-31
+                                                 (2, 2, 30, 2, 2, 2, [(6, 4), (3, 2)]),           # test.py:111 channel counts
+                                                 (2, 2, 71, 2, 2, 2, [(6, 4), (3, 2)]),
+                                                 (2, 16, 16, 100, 1, 2, [(40, 40)]),
+                                                 (1, 24, 16, 50, 2, 4, [(80, 80), (20, 20)])])
+def test_ms_deform_attn_backward_operator(N, M, D, Lq, L, P, shapes):
+    """ms_deform_attn_backward (ms_deform_attn.h:37-60) against autograd through the checker the reference itself uses
+    (test.py:85-108 compares against numerical gradients of the same function)."""
+    from b200 import capi
+    sh = torch.as_tensor(shapes, dtype=torch.long).cuda()
+    lsi = torch.cat((sh.new_zeros((1,)), sh.prod(1).cumsum(0)[:-1]))
+    S = int(sh.prod(1).sum())
+    value, loc, aw = _op_inputs(N, S, M, D, Lq, L, P, torch.float32, seed=7)
+    value = value * 100.0                                                # O(1) values: gradients well above fp32 noise
+    loc = (loc * 1.2 - 0.1).contiguous()                                 # some samples fall outside the image
+    g = torch.Generator(device="cuda").manual_seed(1)
+    grad_out = torch.randn(N, Lq, M * D, device="cuda", generator=g)
+    gv, gl, ga = capi.ms_deform_attn_backward(value, sh, lsi, loc, aw, grad_out, im2col_step=64)
+    _, rv, rl, ra = _autograd_reference(value, shapes, loc, aw, grad_out)
+    for got, ref, what in ((gv, rv, "grad_value"), (gl, rl, "grad_sampling_loc"), (ga, ra, "grad_attn_weight")):
+        err = (got.double().cpu() - ref).abs().max().item()
+        assert err <= 2e-5 * max(1.0, ref.abs().max().item()), (what, err)
+
+
+def _reference_ops_package():
+    """The reference's models/ops Python package (functions/, modules/) from /root/reference or its staged copy
+    baseline/_ref, with OUR MultiScaleDeformableAttention module standing in for the compiled one."""
+    import importlib
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    import ref_import
+    if not ref_import.available():
+        pytest.skip("no reference tree (neither /root/reference nor baseline/_ref)")
+    mod = sys.modules.get("MultiScaleDeformableAttention")
+    if mod is None or not hasattr(mod, "ms_deform_attn_forward"):
+        sys.modules.pop("MultiScaleDeformableAttention", None)
+        importlib.import_module("MultiScaleDeformableAttention")          # lw-detr_b200/MultiScaleDeformableAttention.py
+    ops = os.path.join(ref_import.REF, "models", "ops")
+    for k in [k for k in sys.modules if k == "functions" or k.startswith("functions.")]:
+        del sys.modules[k]
+    sys.path.insert(0, ops)
+    try:
+        from functions.ms_deform_attn_func import MSDeformAttnFunction, ms_deform_attn_core_pytorch
+    finally:
+        sys.path.remove(ops)
+    return MSDeformAttnFunction, ms_deform_attn_core_pytorch
+
+
+def test_reference_msdeformattnfunction_binds_to_this_library():
+    """models/ops/test.py replayed with the reference's OWN autograd Function and checker, unmodified
+    (functions/ms_deform_attn_func.py:23-50): `import MultiScaleDeformableAttention as MSDA` resolves to the drop-in
+    module, forward and backward run on the sm_100a kernels."""
+    Fn, core = _reference_ops_package()
+    N, M, D, Lq, L, P = 1, 2, 2, 2, 2, 2                                   # test.py:27-31
+    shapes = torch.as_tensor([(6, 4), (3, 2)], dtype=torch.long).cuda()
+    lsi = torch.cat((shapes.new_zeros((1,)), shapes.prod(1).cumsum(0)[:-1]))
+    S = sum([(H * W).item() for H, W in shapes])
+    torch.manual_seed(3)
+    for cast in (lambda t: t.double(), lambda t: t):                       # check_forward_equal_with_pytorch_double / _float
+        value = torch.rand(N, S, M, D).cuda() * 0.01
+        loc = torch.rand(N, Lq, M, L, P, 2).cuda()
+        aw = torch.rand(N, Lq, M, L, P).cuda() + 1e-5
+        aw /= aw.sum(-1, keepdim=True).sum(-2, keepdim=True)
+        ref = core(cast(value).permute(0, 2, 3, 1), shapes, cast(loc), cast(aw)).detach().cpu()     # this fork's checker takes [N, M, D, S]
+        out = Fn.apply(cast(value), shapes, lsi, cast(loc), cast(aw), 2).detach().cpu()
+        assert torch.allclose(out, ref, rtol=1e-2, atol=1e-3)              # test.py:82
+        assert (out - ref).abs().max().item() < 1e-7
+    # gradients through the reference Function (test.py:85-108 uses gradcheck on the same call)
+    value = (torch.rand(N, S, M, 8).cuda()).requires_grad_(True)
+    loc = torch.rand(N, Lq, M, L, P, 2).cuda().requires_grad_(True)
+    aw = (torch.rand(N, Lq, M, L, P).cuda() + 1e-5)
+    aw = (aw / aw.sum(-1, keepdim=True).sum(-2, keepdim=True)).detach().requires_grad_(True)
+    out = Fn.apply(value, shapes, lsi, loc, aw, 2)
+    gout = torch.randn_like(out)
+    out.backward(gout)
+    _, rv, rl, ra = _autograd_reference(value, [(6, 4), (3, 2)], loc, aw, gout)
+    assert (value.grad.double().cpu() - rv).abs().max().item() < 1e-5
+    assert (loc.grad.double().cpu() - rl).abs().max().item() < 1e-4
+    assert (aw.grad.double().cpu() - ra).abs().max().item() < 1e-5

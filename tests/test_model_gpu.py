@@ -9,16 +9,25 @@ import torch
 pytestmark = pytest.mark.gpu
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
 
-# Stated tolerances (fp32 oracle vs the 16-bit CUDA path), protocol of SURVEY.md 8c: 3x the deviation of a
-# torch.autocast(fp16 / bf16) run of the same forward on the same synthetic weights, two-stage indices forced
-# (calibration measured on tiny/small B=2 in the build container, see DESIGN.md "Parity"):
-#   autocast fp16: memory 9.1e-4, score 4.5e-3, dec 1.2e-3, logits rel-L2 6.1e-4 / max-abs 7.1e-3, boxes 2.8e-4
-#   autocast bf16: memory 7.3e-3, score 3.5e-2, dec 1.0e-2, logits rel-L2 5.0e-3 / max-abs 6.6e-2, boxes 2.4e-3
-# "block" (ViT residual stream) is looser than 3x autocast because this path keeps the residual stream in
-# 16 bits between blocks while autocast keeps it in fp32.
+# Tolerances (fp32 oracle vs the 16-bit CUDA path, two-stage indices forced = SURVEY.md 8c tier T2).  Two candidate bars:
+#   SURVEY  - SURVEY.md 8c "Stated tolerances"
+#   AC3     - 3x the deviation of a torch.autocast run of the same forward on the same synthetic weights (the
+#             reference's own low-precision mode; calibrated on tiny/small B=2 in the build container)
+# The test asserts the TIGHTER of the two wherever the CUDA path meets it on every config and batch size measured on the
+# B200 (profiles/r02_parity_baseline.json); the two exceptions are stated with their reason.
+#                      SURVEY        AC3        asserted   measured max (all configs, B up to 64)
+#   fp16 logits rel-L2 1.5e-3        1.8e-3     1.5e-3     see DESIGN.md section 4
+#   fp16 logits max    1.5e-2        2.1e-2     1.5e-2
+#   fp16 boxes  max    2.0e-4        8.5e-4     5.0e-4  <- SURVEY's 2e-4 came from autocast, which keeps the residual stream and the
+#                                                          decoder hidden state in fp32; this path stores both in fp16 between kernels
+#                                                          (2^-11 relative per store, 3 decoder layers + bbox MLP): measured 2.0-2.6e-4
+#   bf16 logits rel-L2 6.0e-3        1.5e-2     6.0e-3
+#   bf16 logits max    8.0e-2        2.0e-1     8.0e-2
+#   bf16 boxes  max    1.5e-3        7.0e-3     3.5e-3  <- same reason with 2^-8 stores: measured 1.5-2.5e-3 (aux layers highest)
+# "block" (ViT residual stream) is looser than 3x autocast for the same reason (16-bit residual stream between blocks).
 TOL = {
-    torch.float16: dict(block=2e-3, memory=2.7e-3, score=1.4e-2, logits_rel=1.8e-3, logits_abs=2.1e-2, boxes=8.5e-4, dec=3.6e-3),
-    torch.bfloat16: dict(block=1.5e-2, memory=2.2e-2, score=1.0e-1, logits_rel=1.5e-2, logits_abs=2.0e-1, boxes=7e-3, dec=3e-2),
+    torch.float16: dict(block=2e-3, memory=2.7e-3, score=1.4e-2, logits_rel=1.5e-3, logits_abs=1.5e-2, boxes=5e-4, dec=3.6e-3),
+    torch.bfloat16: dict(block=1.5e-2, memory=2.2e-2, score=1.0e-1, logits_rel=6e-3, logits_abs=8e-2, boxes=3.5e-3, dec=3e-2),
 }
 CASES = [("tiny", 2), ("small", 2), ("medium", 1), ("large", 1), ("xlarge", 1)]
 
@@ -115,3 +124,36 @@ def test_full_size_batch_is_consistent_with_small_batches(name, batch, dt):
             dl = (small["pred_logits"][rows] - big["pred_logits"][lo:lo + 2][rows]).abs().max().item()
             db = (small["pred_boxes"][rows] - big["pred_boxes"][lo:lo + 2][rows]).abs().max().item()
             assert dl <= tol_l and db <= tol_b, (dl, db)
+
+
+# BASELINE.json configs[1..4]: the batch sizes bench.py measures.  GEMM tile choice, persistent-CTA work splits, attention
+# grids and the deformable-attention item walk all depend on the batch, so the benchmarked code path is compared with the
+# oracle image by image (the oracle runs in chunks of 4 images; it is per-image independent).
+BASELINE_CASES = [("small", 32, torch.float16), ("medium", 64, torch.bfloat16), ("large", 32, torch.float16), ("xlarge", 16, torch.float16)]
+
+
+@pytest.mark.parametrize("name,batch,dt", BASELINE_CASES)
+def test_parity_at_baseline_batch_sizes(name, batch, dt):
+    import json
+    import parity_report
+    torch.set_num_threads(min(32, os.cpu_count() or 1))
+    rep = parity_report.baseline_parity(name, batch, dt, chunk=4)
+    out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    try:
+        os.makedirs(out, exist_ok=True)
+        with open(os.path.join(out, "parity_baseline_%s.json" % name), "w") as f:
+            json.dump(rep, f, indent=1)
+    except OSError:
+        pass
+    tol = TOL[dt]
+    assert rep["topk_echo_ok"] and rep["finite"]
+    assert rep["memory_rel_l2_max"] <= tol["memory"], rep                      # T1, worst image
+    assert rep["enc_score_maxabs"] <= tol["score"], rep
+    assert rep["logits_rel_l2_max"] <= tol["logits_rel"], rep                  # T2, worst image
+    assert rep["logits_maxabs"] <= tol["logits_abs"] and rep["aux_logits_maxabs"] <= tol["logits_abs"], rep
+    assert rep["enc_logits_maxabs"] <= tol["logits_abs"], rep
+    assert rep["boxes_maxabs"] <= tol["boxes"] and rep["aux_boxes_maxabs"] <= tol["boxes"] and rep["enc_boxes_maxabs"] <= tol["boxes"], rep
+    assert rep["set_agreement_min"] >= 0.95, rep                               # T3, every image
+    if "slot_aligned_enc_boxes_maxabs" in rep:
+        assert rep["slot_aligned_enc_boxes_maxabs"] <= 2 * tol["boxes"], rep
+        assert rep["slot_aligned_enc_logits_maxabs"] <= 2 * tol["logits_abs"], rep

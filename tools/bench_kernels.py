@@ -49,22 +49,27 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--iters", type=int, default=30)
     ap.add_argument("--out", default=None)
+    ap.add_argument("--only", default=None, help="comma list of kernels: msda_forward,window_attention,global_attention")
+    ap.add_argument("--configs", default=None, help="comma list of configs (default: the four BASELINE configs)")
     a = ap.parse_args()
     hbm, tflops, src = peaks()
     flush = torch.zeros(64 * 1024 * 1024, device="cuda", dtype=torch.float32)
     res = []
     g = torch.Generator(device="cuda").manual_seed(0)
     cases = [("small", 32, torch.float16), ("medium", 64, torch.bfloat16), ("large", 32, torch.float16), ("xlarge", 16, torch.float16)]
+    only = set(a.only.split(",")) if a.only else None
+    if a.configs:
+        cases = [c for c in cases if c[0] in a.configs.split(",")]
     for name, B, dt in cases:
         cfg = CONFIGS[name]
         d, M, L, P, nq, S = cfg.hidden_dim, cfg.ca_nheads, cfg.n_levels, cfg.dec_n_points, cfg.num_queries, cfg.memory_len
         # ---- deformable attention core (one decoder layer)
-        value = torch.randn(B * S, 3 * d, device="cuda", generator=g).to(dt)
+        value = torch.randn(B, 3, M, S, 16, device="cuda", generator=g).to(dt)      # head-major, three layers' values in one buffer
         ol = (torch.randn(B * nq, 3 * M * L * P, device="cuda", generator=g) * 1.5).to(dt)
         ref = torch.rand(B * nq, 4, device="cuda", generator=g) * torch.tensor([0.9, 0.9, 0.4, 0.4], device="cuda") + 0.05
         out = torch.empty(B * nq, d, device="cuda", dtype=dt)
-        fn = lambda: capi.msda_forward(value[:, d:2 * d], ol, ref, out, B, S, nq, M, L, P, list(cfg.level_shapes))
-        med, best = timed(fn, a.iters, flush)
+        fn = lambda: capi.msda_forward(value[:, 1], ol, ref, out, B, S, nq, M, L, P, list(cfg.level_shapes), v_image_stride=3 * M * S * 16)
+        med, best = timed(fn, a.iters, flush) if (only is None or "msda_forward" in only) else (float("nan"), float("nan"))
         elt = 2
         algo = min(B * S * d, B * nq * M * L * P * 4 * 16) * elt + B * nq * M * L * P * 3 * elt + B * nq * d * elt
         res.append({"kernel": "msda_forward", "config": "%s B=%d %s" % (name, B, str(dt)[6:]), "us_median": med, "us_best": best,
@@ -76,6 +81,8 @@ def main():
         qkv = torch.randn(B * T, 3 * C, device="cuda", generator=g).to(dt)
         att = torch.empty(B * T, C, device="cuda", dtype=dt)
         for kind, nseq, seqlen in (("window_attention", 16 * B, T // 16), ("global_attention", B, T)):
+            if only is not None and kind not in only:
+                continue
             fn = lambda: capi.attention(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], att, nseq, seqlen, heads, dh, dh ** -0.5)
             med, best = timed(fn, a.iters, flush)
             algo = B * T * 4 * C * elt

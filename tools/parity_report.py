@@ -121,3 +121,65 @@ if __name__ == "__main__":
     if a.out:
         with open(a.out, "w") as f:
             json.dump(reps, f, indent=1)
+
+
+def baseline_parity(name, batch, dtype, chunk=4, wseed=1, iseed=11):
+    """Oracle comparison of EVERY image of a BASELINE.json batch (configs[1..4]) through the C ABI: the oracle runs in
+    chunks of `chunk` images (it is batch-independent per image), the engine runs the whole batch at once - i.e. with
+    the GEMM tilings, attention grids and persistent-CTA splits bench.py measures.  T2: two-stage indices forced to the
+    oracle's, outputs compared element-wise; T3: free-running selected-set agreement per image."""
+    cfg = CONFIGS[name]
+    sd = synth_state_dict(cfg, wseed)
+    x = synth_images(batch, iseed)
+    refs, topks, mems, scores = [], [], [], []
+    for lo in range(0, batch, chunk):
+        inter = {}
+        r = orc.forward(sd, cfg, x[lo:lo + chunk], inter=inter)
+        refs.append(r)
+        topks.append(inter["topk"])
+        mems.append(inter["memory"])
+        scores.append(inter["enc_score"])
+    topk = torch.cat(topks)
+    cat = lambda key: torch.cat([r[key] for r in refs])
+    ref = {"pred_logits": cat("pred_logits"), "pred_boxes": cat("pred_boxes"),
+           "enc_logits": torch.cat([r["enc_outputs"]["pred_logits"] for r in refs]),
+           "enc_boxes": torch.cat([r["enc_outputs"]["pred_boxes"] for r in refs]),
+           "aux_logits": [torch.cat([r["aux_outputs"][i]["pred_logits"] for r in refs]) for i in range(cfg.dec_layers - 1)],
+           "aux_boxes": [torch.cat([r["aux_outputs"][i]["pred_boxes"] for r in refs]) for i in range(cfg.dec_layers - 1)]}
+    eng = capi.Engine(cfg, dtype)
+    eng.load_state_dict(sd)
+    xg = x.cuda()
+    S, d, nq = cfg.memory_len, cfg.hidden_dim, cfg.num_queries
+    eng.capture("level%d" % (cfg.n_levels - 1), batch * S * d)
+    eng.capture("enc_score", batch * S)
+    forced = eng.forward(xg, topk_override=topk)
+    torch.cuda.synchronize()
+    got = eng.capture_results()
+    eng.clear_captures()
+    mem = got["level%d" % (cfg.n_levels - 1)].reshape(batch, S, d)
+    memref = torch.cat(mems)
+    per_img = lambda a, b: ((a - b).flatten(1).norm(dim=1) / (b.flatten(1).norm(dim=1) + 1e-12))
+    rep = {"config": name, "batch": batch, "dtype": str(dtype).replace("torch.", "")}
+    rep["memory_rel_l2_max"] = per_img(mem, memref).max().item()
+    rep["enc_score_maxabs"] = (got["enc_score"].reshape(batch, S) - torch.cat(scores)).abs().max().item()
+    rep["topk_echo_ok"] = bool((forced["topk_index"].cpu().long() == topk).all())
+    fl, fb = forced["pred_logits"].cpu(), forced["pred_boxes"].cpu()
+    rep["logits_rel_l2_max"] = per_img(fl, ref["pred_logits"]).max().item()       # worst image
+    rep["logits_rel_l2"] = rel_l2(fl, ref["pred_logits"])
+    rep["logits_maxabs"] = (fl - ref["pred_logits"]).abs().max().item()
+    rep["boxes_maxabs"] = (fb - ref["pred_boxes"]).abs().max().item()
+    rep["enc_logits_maxabs"] = (forced["enc_outputs"]["pred_logits"].cpu() - ref["enc_logits"]).abs().max().item()
+    rep["enc_boxes_maxabs"] = (forced["enc_outputs"]["pred_boxes"].cpu() - ref["enc_boxes"]).abs().max().item()
+    rep["aux_logits_maxabs"] = max((forced["aux_outputs"][i]["pred_logits"].cpu() - ref["aux_logits"][i]).abs().max().item() for i in range(cfg.dec_layers - 1))
+    rep["aux_boxes_maxabs"] = max((forced["aux_outputs"][i]["pred_boxes"].cpu() - ref["aux_boxes"][i]).abs().max().item() for i in range(cfg.dec_layers - 1))
+    free = eng.forward(xg)
+    torch.cuda.synchronize()
+    ti = free["topk_index"].cpu().long()
+    rep["set_agreement_min"] = min(len(set(ti[b].tolist()) & set(topk[b].tolist())) / float(nq) for b in range(batch))
+    rep["finite"] = bool(torch.isfinite(free["pred_logits"]).all() and torch.isfinite(free["pred_boxes"]).all())
+    same = (ti == topk)
+    if same.any():
+        rep["slot_aligned_enc_boxes_maxabs"] = (free["enc_outputs"]["pred_boxes"].cpu() - ref["enc_boxes"])[same].abs().max().item()
+        rep["slot_aligned_enc_logits_maxabs"] = (free["enc_outputs"]["pred_logits"].cpu() - ref["enc_logits"])[same].abs().max().item()
+    eng.close()
+    return rep

@@ -1,7 +1,8 @@
 """Import the UNMODIFIED reference (Atten4Vis/LW-DETR at /root/reference) in the build container.
 
-Only used by the golden-vector generator (tools/make_goldens.py) and by CPU tests that are skipped
-when /root/reference is absent (it never exists on the GPU box).  Three third-party modules the
+Used by the golden-vector generator (tools/make_goldens.py), by CPU tests that are skipped when no
+reference tree is available, and by bench.py's reference arm / cpu_baseline leg, which on the GPU box import
+the byte-identical copy staged under baseline/_ref/ by tools/vendor_reference.py (git-ignored).  Three third-party modules the
 reference imports are missing offline and are shimmed:
   * timm.models.layers: DropPath (identity at eval), Mlp (fc1 -> GELU(erf) -> fc2), trunc_normal_
   * fairscale.nn.checkpoint.checkpoint_wrapper (never invoked: use_act_checkpoint=False)
@@ -13,7 +14,9 @@ import os
 import sys
 import types
 
-REF = os.environ.get("LWDETR_REFERENCE", "/root/reference")
+_VENDORED = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "baseline", "_ref")
+# /root/reference in the build container; on the GPU box the unmodified copy staged by tools/vendor_reference.py
+REF = os.environ.get("LWDETR_REFERENCE") or ("/root/reference" if os.path.isdir("/root/reference/models") else _VENDORED)
 
 
 def available():
