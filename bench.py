@@ -220,15 +220,23 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    # weights: rank 0 materialises them, one NCCL broadcast of the flat arena at init
+    # weights: rank 0 holds the real ones, every other rank packs DIFFERENT (seeded by its rank) weights of the same shapes -
+    # that only fixes the arena layout - and ONE ncclBroadcast of the packed arena through the C ABI
+    # (lwdetr_broadcast_weights) makes them rank 0's.  No other collective touches the data path.
     model = LWDETR(cfg, compute_dtype=dt).eval()
-    if rank == 0:
-        model.load_state_dict(synth_state_dict(cfg, 1), strict=True)
+    model.load_state_dict(synth_state_dict(cfg, 1 if rank == 0 else 1000 + rank), strict=True)
     model.to(dev)
-    from b200.dist import broadcast_module_weights
-    broadcast_module_weights(model, src=0)
-    model.assume_frozen = True
     eng = model.engine()
+    model.assume_frozen = True
+    bcast_bytes, replicas_agree = 0, None
+    if world > 1:
+        from b200.dist import broadcast_engine_weights
+        bcast_bytes = broadcast_engine_weights(eng, dev, src=0)
+        probe = eng.forward(synth_images(1, seed=12345).to(dev), want_aux=False)
+        sig = torch.stack([probe["pred_logits"].double().sum(), probe["pred_boxes"].double().sum()])
+        allsig = [torch.empty_like(sig) for _ in range(world)]
+        dist.all_gather(allsig, sig)
+        replicas_agree = bool(all(torch.equal(s_, allsig[0]) for s_ in allsig))     # bit-identical replicas after the broadcast
     eng.set_option("cuda_graph", 0 if a.no_graph else 1)
     eng.set_option("pdl", 0 if a.no_pdl else 1)
     # inputs: two distinct device batches (fp32, 4.9 MB/image => larger than the 126 MB L2 at batch >= 26)
@@ -423,7 +431,7 @@ def main():
         cfgd.update({"l2": "no flush needed: inputs alternate between two fp32 batches of %.0f MB and one step streams %.1f GB of "
                            "activations and weights through the kernels (>> 126 MB L2), so nothing survives from step to step"
                            % (in_bytes / 1e6, step_bytes / 1e9),
-                     "cuda_graph": not a.no_graph, "pdl": not a.no_pdl, "model_gflop_per_image": FLOPS_PER_IMAGE[cfg_name] / 1e9,
+                     "cuda_graph": not a.no_graph, "pdl": not a.no_pdl, "weight_broadcast_bytes": bcast_bytes, "replicas_bit_identical": replicas_agree, "model_gflop_per_image": FLOPS_PER_IMAGE[cfg_name] / 1e9,
                      "whole_model_tensor_frac_of_sustained": value * FLOPS_PER_IMAGE[cfg_name] / (peaks()["bf16_tflops_sustained"] * 1e12)})
         print(json.dumps({
             "metric": "images/sec (640x640)", "value": value, "unit": "images/s", "n_gpus": world, "steps": a.steps, "warmup": warmup,

@@ -153,7 +153,8 @@ typedef struct {
   int32_t* topk_index; /* [B, nq] two-stage selection (token index per query slot) or NULL */
 } lwdetr_aux_out;
 
-/* One handle per (device, config, compute dtype); not thread-safe per handle. */
+/* One handle per (device, config, compute dtype); not thread-safe per handle.  The handle binds to the CUDA device
+ * that is current at creation; every later call switches to that device for its duration. */
 LWDETR_API int lwdetr_create(const lwdetr_config* cfg, int dtype, lwdetr_handle** out);
 LWDETR_API void lwdetr_destroy(lwdetr_handle* h);
 
@@ -171,7 +172,34 @@ LWDETR_API int lwdetr_forward(lwdetr_handle* h, const void* images, int images_f
                               float* pred_boxes, const lwdetr_aux_out* aux, const int32_t* topk_override,
                               void* stream);
 
-/* options: "cuda_graph" (0/1, default 1), "fuse_layernorm" (0/1, default 1), "pdl" (0/1, default 1: programmatic dependent
+/* The same forward with the two input forms the callers on either side of the path use:
+ *   format LWDETR_IN_U8_NHWC: images is DEVICE uint8 [B, S, S, 3] - the output of an image decoder + resize.  ToTensor's /255
+ *     and Normalize(mean, std) (demo/demo.py:146-159, datasets/transforms.py:223-252) are fused into the patch gather:
+ *     (x/255 - mean[c]) / std[c]; the fp32 NCHW image never exists (4x fewer input bytes over PCIe and HBM).
+ *   padding_mask: DEVICE bool [B, S, S] (True = padded pixel), the NestedTensor mask of a padded / mixed-size batch
+ *     (util/misc.py:317-339), or NULL.  Implements backbone.py:153-158 (nearest resize per level), transformer.py:
+ *     86-89,112-123 (per-image proposals, masked memory rows), :189-196,352-355 (valid ratios on the reference boxes) and
+ *     ops/modules/ms_deform_attn.py:114-115 (masked value rows).  The ViT itself takes no mask (backbone.py:145). */
+enum { LWDETR_IN_F32_NCHW = 0, LWDETR_IN_16_NCHW = 1, LWDETR_IN_U8_NHWC = 2 };
+typedef struct {
+  const void* images;
+  int32_t format;
+  const uint8_t* padding_mask;
+  float mean[3], std[3];        /* LWDETR_IN_U8_NHWC only */
+} lwdetr_input;
+LWDETR_API int lwdetr_forward_ex(lwdetr_handle* h, const lwdetr_input* input, int B, float* pred_logits, float* pred_boxes,
+                                 const lwdetr_aux_out* aux, const int32_t* topk_override, void* stream);
+
+/* Multi-GPU init: ONE ncclBroadcast of the packed weight arena from rank `root`, stream-ordered on
+ * `stream`; the only collective of the path (images shard across ranks as independent replicas, nothing on the hot path).
+ * Every rank first calls lwdetr_load_weights with tensors of the right shapes (any values on the non-root ranks): that
+ * fixes the arena layout, which is a function of (config, dtype) only; the call verifies that the arena sizes agree.
+ * `nccl_comm` is an ncclComm_t of a communicator the caller created (one rank per GPU); NCCL is resolved at run time
+ * from the libnccl already loaded in the process (or dlopen("libnccl.so.2")), the library does not link it. */
+LWDETR_API int lwdetr_broadcast_weights(lwdetr_handle* h, void* nccl_comm, int root, void* stream);
+LWDETR_API int64_t lwdetr_weight_arena_bytes(lwdetr_handle* h);
+
+/* options: "cuda_graph" (0/1, default 0: the caller opts in after warm-up), "fuse_layernorm" (0/1, default 1), "pdl" (0/1, default 1: programmatic dependent
  * launch of every kernel; process-wide) */
 LWDETR_API int lwdetr_set_option(lwdetr_handle* h, const char* name, int value);
 

@@ -33,6 +33,9 @@ _SIGNATURES = {
     "lwdetr_destroy": (None, [_vp]),
     "lwdetr_load_weights": (_i, [_vp, _i, _vp, _vp, _vp]),
     "lwdetr_forward": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp]),
+    "lwdetr_broadcast_weights": (_i, [_vp, _vp, _i, _vp]),
+    "lwdetr_weight_arena_bytes": (_i64, [_vp]),
+    "lwdetr_forward_ex": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp, _vp]),
     "lwdetr_set_option": (_i, [_vp, ctypes.c_char_p, _i]),
     "lwdetr_add_capture": (_i, [_vp, ctypes.c_char_p, _vp, _i64]),
     "lwdetr_capture_result": (_i64, [_vp, _i]),
@@ -83,9 +86,9 @@ def dtype_code(torch_dtype):
     raise RuntimeError("lwdetr_b200 computes in float16 or bfloat16, got %s" % torch_dtype)
 
 
-def stream_ptr():
+def stream_ptr(device=None):
     import torch
-    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
 
 def gemm(A, W, out, bias=None, gamma=None, resid=None, resid_mod=0, act=ACT_NONE, M=None, K=None, N=None,
@@ -236,6 +239,14 @@ class ConfigStruct(ctypes.Structure):
                                               "dec_layers", "dim_feedforward", "num_classes", "group_detr", "img_size")]
 
 
+class InputDesc(ctypes.Structure):
+    _fields_ = [("images", _vp), ("format", ctypes.c_int32), ("padding_mask", _vp), ("mean", ctypes.c_float * 3), ("std", ctypes.c_float * 3)]
+
+
+IN_F32_NCHW, IN_16_NCHW, IN_U8_NHWC = 0, 1, 2
+IMAGENET_MEAN, IMAGENET_STD = (0.485, 0.456, 0.406), (0.229, 0.224, 0.225)      # demo/demo.py:150-153, datasets/coco.py
+
+
 class AuxOut(ctypes.Structure):
     _fields_ = [(n, _vp) for n in ("aux_logits", "aux_boxes", "enc_logits", "enc_boxes", "topk_index")]
 
@@ -260,14 +271,16 @@ def config_struct(cfg):
 class Engine:
     """Owns one lwdetr_handle: packed weights + kernel schedule on the current CUDA device."""
 
-    def __init__(self, cfg, dtype):
+    def __init__(self, cfg, dtype, device=None):
         import torch
         if not torch.cuda.is_available():
             raise RuntimeError("lwdetr_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
         self.cfg, self.dtype = cfg, dtype
         self._h = _vp()
         cs = config_struct(cfg)
-        check(lib().lwdetr_create(ctypes.byref(cs), dtype_code(dtype), ctypes.byref(self._h)), "lwdetr_create")
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        with torch.cuda.device(self.device):      # the handle binds to the device current at creation
+            check(lib().lwdetr_create(ctypes.byref(cs), dtype_code(dtype), ctypes.byref(self._h)), "lwdetr_create")
         self._captures = []
 
     def close(self):
@@ -297,19 +310,46 @@ class Engine:
         check(lib().lwdetr_load_weights(self._h, n, ctypes.cast(c_names, _vp), ctypes.cast(c_ptrs, _vp),
                                         ctypes.cast(c_numel, _vp)), "lwdetr_load_weights")
 
+    def broadcast_weights(self, nccl_comm, root=0):
+        """One ncclBroadcast of the packed arena from rank `root` (nccl_comm: integer ncclComm_t, see b200/dist.py)."""
+        check(lib().lwdetr_broadcast_weights(self._h, ctypes.c_void_p(nccl_comm), int(root), stream_ptr()), "lwdetr_broadcast_weights")
+
+    def arena_bytes(self):
+        return int(lib().lwdetr_weight_arena_bytes(self._h))
+
     def set_option(self, name, value):
         check(lib().lwdetr_set_option(self._h, name.encode(), int(value)), "lwdetr_set_option")
 
-    def forward(self, images, want_aux=True, topk_override=None):
-        """images: CUDA [B,3,S,S] fp32 or compute dtype.  Returns the reference's output dict (fp32 CUDA tensors)."""
+    def forward(self, images, want_aux=True, topk_override=None, mask=None, mean=IMAGENET_MEAN, std=IMAGENET_STD):
+        """images: CUDA [B,3,S,S] fp32 / compute dtype, or CUDA uint8 [B,S,S,3] (HWC, normalised on the fly with mean/std);
+        mask: CUDA bool [B,S,S] (True = padded pixel) or None.  Returns the reference's output dict (fp32 CUDA tensors)."""
         import torch
         if images.device.type != "cuda":
             raise RuntimeError("lwdetr_b200: images must be CUDA tensors")
-        if images.dim() != 4 or images.shape[1] != 3 or images.shape[2] != self.cfg.img_size or images.shape[3] != self.cfg.img_size:
-            raise RuntimeError("lwdetr_b200: expected images [B, 3, %d, %d], got %s" % (self.cfg.img_size, self.cfg.img_size, tuple(images.shape)))
-        if images.dtype not in (torch.float32, self.dtype):
-            images = images.float()
+        if images.device != self.device:
+            raise RuntimeError("lwdetr_b200: images are on %s but the engine lives on %s" % (images.device, self.device))
+        S = self.cfg.img_size
+        desc = InputDesc()
+        if images.dtype == torch.uint8:
+            if images.dim() != 4 or tuple(images.shape[1:]) != (S, S, 3):
+                raise RuntimeError("lwdetr_b200: uint8 images must be [B, %d, %d, 3] (HWC), got %s" % (S, S, tuple(images.shape)))
+            desc.format = IN_U8_NHWC
+            for c in range(3):
+                desc.mean[c], desc.std[c] = float(mean[c]), float(std[c])
+        else:
+            if images.dim() != 4 or images.shape[1] != 3 or images.shape[2] != S or images.shape[3] != S:
+                raise RuntimeError("lwdetr_b200: expected images [B, 3, %d, %d], got %s" % (S, S, tuple(images.shape)))
+            if images.dtype not in (torch.float32, self.dtype):
+                images = images.float()
+            desc.format = IN_F32_NCHW if images.dtype == torch.float32 else IN_16_NCHW
         images = images.contiguous()
+        mk = None
+        if mask is not None:
+            if tuple(mask.shape) != (images.shape[0], S, S):
+                raise RuntimeError("lwdetr_b200: mask must be [B, %d, %d], got %s" % (S, S, tuple(mask.shape)))
+            mk = mask.to(device=self.device, dtype=torch.bool).contiguous()
+        desc.images = images.data_ptr()
+        desc.padding_mask = mk.data_ptr() if mk is not None else None
         B, nq, nc, nl = images.shape[0], self.cfg.num_queries, self.cfg.num_classes, self.cfg.dec_layers
         dev = images.device
         logits = torch.empty(B, nq, nc, device=dev, dtype=torch.float32)
@@ -331,9 +371,9 @@ class Engine:
         ov = None
         if topk_override is not None:
             ov = topk_override.to(device=dev, dtype=torch.int32).contiguous()
-        check(lib().lwdetr_forward(self._h, ptr(images), 1 if images.dtype == torch.float32 else 0, B, ptr(logits), ptr(boxes),
-                                   ctypes.byref(aux) if aux is not None else None, ptr(ov), stream_ptr()), "lwdetr_forward")
-        self._last_inputs = (images, ov)        # keep alive until the stream has consumed them
+        check(lib().lwdetr_forward_ex(self._h, ctypes.byref(desc), B, ptr(logits), ptr(boxes),
+                                      ctypes.byref(aux) if aux is not None else None, ptr(ov), stream_ptr(self.device)), "lwdetr_forward_ex")
+        self._last_inputs = (images, ov, mk)    # keep alive until the stream has consumed them
         return res
 
     # ---- debug captures -------------------------------------------------------------------------

@@ -383,7 +383,19 @@ static int dispatch(const AttnArgs& a, int dh, cudaStream_t st) {
   return -2;
 }
 
-int attention_tc_launch(int dtype, const AttnArgs& a, int dh, int C, cudaStream_t st);   // attn_tc.cu
+int attention_tc_launch(int dtype, const AttnArgs& a, int dh, int C, cudaStream_t st);      // attn_tc.cu
+int attention_slots_launch(int dtype, const AttnArgs& a, int dh, int C, cudaStream_t st);   // attn_slots.cu
+
+// Slot kernel (attn_slots.cu: tcgen05, one thread per row, partly polynomial exp2) for packed qkv:
+//   0 = never, 1 (default) = head dim 16 always + head dim 32 for sequences of <= 128 tokens (the ViT windows),
+//   2 = head dim 32 for every sequence length as well.  Environment override for A/B measurements only.
+static int slots_policy() {
+  static int v = [] {
+    const char* e = getenv("LWDETR_B200_ATTN_SLOTS");
+    return e ? atoi(e) : 1;
+  }();
+  return v;
+}
 
 // 0 = mma.sync flash kernel everywhere, 1 = tcgen05 kernel for long packed-qkv sequences with dh >= 32 (default; measured
 // 18-22 % faster there, 10 % slower at dh = 16 where the mma.sync kernel's 6 warps per scheduler hide latency better),
@@ -401,6 +413,9 @@ int attention_launch(int dtype, const AttnArgs& a, int dh, cudaStream_t st) {
   const long long dv = (static_cast<const char*>(a.v) - static_cast<const char*>(a.q)) / 2;
   const bool packed = dk > 0 && dv == 2 * dk && a.ldq == a.ldk && a.ldq == a.ldv && dk == static_cast<long long>(a.heads) * dh &&
                       a.ldq >= 3 * dk && (reinterpret_cast<uintptr_t>(a.q) & 15) == 0;
+  const int sp = slots_policy();
+  if (packed && sp > 0 && (dh == 16 || (dh == 32 && (a.seqlen <= 128 || sp >= 2))))
+    return attention_slots_launch(dtype, a, dh, static_cast<int>(dk), st);
   const int pol = tc_policy();
   if (packed && a.seqlen >= 512 && (pol == 2 || (pol == 1 && dh >= 32)))
     return attention_tc_launch(dtype, a, dh, static_cast<int>(dk), st);

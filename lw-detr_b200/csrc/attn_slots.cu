@@ -1,0 +1,503 @@
+// tcgen05 / TMA attention for head dims 16 and 32 - the ViT window attention (vit.py:130-137 with B' = 16B, N = 100) and
+// the ViT global attention at head dim 16 (tiny / small; vit.py:201-204).  At these head dims the kernel is bound by the
+// exponentials, not by the tensor core (16 MUFU.EX2 per clock and SM against <= 0.5 k clocks of MMA per 128x128 score
+// tile), so the design is organised around the softmax threads:
+//
+//   * FOUR independent "slots" per CTA (one CTA per SM).  A slot owns one 128-row query tile, its own 128 TMEM columns
+//     (S 64 fp32 | P 32 packed 16-bit | O dh fp32) and its own barrier set; keys are consumed in chunks of 64.
+//   * warps 0-3  : one DRIVER warp per slot (one elected lane): TMA loads of Q and of the K/V chunks straight out of the
+//                  packed [rows, 3C] qkv matrix, and all tcgen05.mma of the slot (S = Q K^T, O += P V with P read from TMEM).
+//   * warps 4-19 : 16 SOFTMAX warps, four per slot, ONE THREAD PER QUERY ROW (tcgen05.ld 32x32b hands thread t row t):
+//                  the row maximum, the lazy rescale decision (FlashAttention-4: the reference maximum only moves when
+//                  exceeded by 2^8) and the row sum need no cross-thread exchange at all.  Every scheduler hosts one
+//                  softmax warp of each slot, i.e. four independent instruction streams.
+//   * exp2: packed fp32x2 FMAs (fma.rn.f32x2) fold scale and max-subtraction; 3 of every 8 pairs take a degree-3
+//     polynomial on the FMA pipe instead of the MUFU (Cody-Waite split by the 1.5*2^23 magic add, exponent patched in with
+//     an integer add; max relative error 7.5e-5, an order of magnitude below the 16-bit rounding of P).  Measured on the
+//     B200 (tools/ubench/softmax_rate.cu, profiles/r02a_ubench_softmax.txt): 0.0486 clk/score/SM against the 0.0625
+//     MUFU floor; more than 3/8 makes the issue slots the bottleneck again.
+//   * setmaxnreg moves registers from the driver warps (56) to the softmax warps (112), which hold a 64-score row chunk.
+//
+// Two work decompositions share the code (template SHARED):
+//   SHARED = true  (sequences longer than one tile, e.g. 1600 tokens): the four slots of a CTA take up to four consecutive
+//                  query tiles of ONE (sequence, head) and walk the keys in lock step over ONE K/V ring filled by slot
+//                  0's driver - K/V are fetched once per CTA, not once per tile.
+//   SHARED = false (sequences of <= 128 tokens, e.g. the 100-token windows): every slot walks its own (sequence, head)
+//                  items with its own small K/V ring; the tail chunk only exponentiates the valid keys (104 instead of 128).
+// CTAs are persistent and walk their items with a fixed stride.
+#include "attn.h"
+#include "launch.h"
+#include "ptx.cuh"
+#include "tma_util.h"
+
+#include <algorithm>
+#include <string>
+#include <type_traits>
+
+namespace lwb {
+namespace sl {
+
+static constexpr int SLOTS = 4;
+static constexpr int BM = 128;                 // query rows per slot
+static constexpr int BK = 64;                  // keys per chunk
+static constexpr int THREADS = 32 * (SLOTS + 4 * SLOTS);
+static constexpr float LAZY_LOG2 = 8.f;        // the row reference maximum moves only when exceeded by more than 2^8
+static constexpr float MAGIC = 12582912.f;     // 1.5 * 2^23
+
+__device__ __forceinline__ uint64_t desc(uint32_t smem_addr, uint32_t sbo_bytes, uint32_t layout_type) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr >> 4) & 0x3FFFu);
+  d |= static_cast<uint64_t>(1) << 16;
+  d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFFu) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(layout_type) << 61;
+  return d;
+}
+// D[tmem] (+)= A[tmem] * B[smem desc]
+__device__ __forceinline__ void mma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void ld_x32(uint32_t taddr, float* v) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,"
+      "%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void st_x16(uint32_t taddr, const uint32_t* r) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+__device__ __forceinline__ void st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ uint64_t pk2(float a, float b) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1,%2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ void upk2(uint64_t v, float& a, float& b) { asm("mov.b64 {%0,%1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+template <int N> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+
+// 2^(s*c - m) for a pair without the MUFU: t = round(s*c - m) + MAGIC by one FFMA2, fraction by a second one, degree-3
+// polynomial, exponent added as an integer.  Arguments below -126 are clamped (the result is then ~1e-38 * poly: harmless).
+__device__ __forceinline__ void exp2_poly_pair(uint64_t s2, uint64_t c2, uint64_t magic_minus_m2, uint64_t negm2, float& e0, float& e1) {
+  const uint64_t t2 = fma2(s2, c2, magic_minus_m2);
+  float t0, t1;
+  upk2(t2, t0, t1);
+  t0 = fmaxf(t0, MAGIC - 126.f);
+  t1 = fmaxf(t1, MAGIC - 126.f);
+  const uint64_t r2 = add2(pk2(t0, t1), pk2(-MAGIC, -MAGIC));
+  const uint64_t u2 = fma2(r2, pk2(-1.f, -1.f), negm2);
+  const uint64_t f2 = fma2(s2, c2, u2);
+  uint64_t p2 = fma2(f2, pk2(0.05517164617776871f, 0.05517164617776871f), pk2(0.2426111251115799f, 0.2426111251115799f));
+  p2 = fma2(p2, f2, pk2(0.6932609677314758f, 0.6932609677314758f));
+  p2 = fma2(p2, f2, pk2(0.9999280571937561f, 0.9999280571937561f));
+  float p0, p1;
+  upk2(p2, p0, p1);
+  e0 = __int_as_float(__float_as_int(p0) + (__float_as_int(t0) << 23));
+  e1 = __int_as_float(__float_as_int(p1) + (__float_as_int(t1) << 23));
+}
+
+struct SlotArgs {
+  void* o;
+  int ldo;
+  int seqlen, nseq, heads;
+  float scale_log2;
+  int C;          // column distance between the q, k and v blocks of the packed matrix
+  int qtiles;     // 128-row query tiles per sequence
+  int ngroups;    // SHARED: CTA items per (sequence, head)
+  int nitems;     // SHARED: nseq*heads*ngroups (CTA items); else nseq*heads*qtiles (slot items)
+};
+
+template <int DH, bool SHARED>
+struct Geo {
+  static constexpr int STAGES = SHARED ? 6 : 4;
+  static constexpr int NRINGS = SHARED ? 1 : SLOTS;
+  static constexpr int Q_BYTES = BM * DH * 2;
+  static constexpr int KV_BYTES = BK * DH * 2;                 // one K (or V) chunk
+  static constexpr int STAGE_BYTES = 2 * KV_BYTES;
+  static constexpr int SMEM_Q = SLOTS * 2 * Q_BYTES;
+  static constexpr int SMEM_RING = NRINGS * STAGES * STAGE_BYTES;
+  static constexpr int NBAR = 7 * SLOTS + 2 * NRINGS * STAGES;
+  static constexpr int SMEM = 1024 + SMEM_Q + SMEM_RING + NBAR * 8 + 64;
+  static constexpr uint32_t SLOT_COLS = 128;                   // S 64 | P 32 | O DH (<= 32): four slots fill the 512 columns
+};
+
+template <typename T, int DH, bool SHARED, uint32_t PMASK>
+__global__ void __launch_bounds__(THREADS, 1) attn_slots_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
+                                                                const SlotArgs p) {
+  using G = Geo<DH, SHARED>;
+  constexpr int STAGES = G::STAGES;
+  constexpr uint32_t PITCH = DH * 2;
+  constexpr uint32_t LAYOUT = DH == 64 ? 2u : (DH == 32 ? 4u : 6u);   // SWIZZLE_128B / 64B / 32B
+  constexpr uint32_t SBO = 8 * PITCH;
+  constexpr uint32_t COL_S = 0, COL_P = 64, COL_O = 96;
+  extern __shared__ uint8_t sl_smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(sl_smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;                                          // [slot][2][Q_BYTES]
+  uint8_t* sRing = sQ + G::SMEM_Q;                             // [ring][stage][K | V]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sRing + G::SMEM_RING);
+  uint64_t* q_full = bars;                 // [slot]
+  uint64_t* s_full = q_full + SLOTS;       // S(j) written by the tensor core
+  uint64_t* s_free = s_full + SLOTS;       // the slot's four softmax warps hold S(j) in registers
+  uint64_t* p_full = s_free + SLOTS;       // P(j) stored (and O rescaled if the reference maximum moved)
+  uint64_t* p_empty = p_full + SLOTS;      // PV(j) completed: P may be overwritten, O is current
+  uint64_t* o_full = p_empty + SLOTS;      // all PV of the item completed
+  uint64_t* o_free = o_full + SLOTS;       // O read out: the next item may overwrite it
+  uint64_t* kv_full = o_free + SLOTS;      // [ring][stage]
+  uint64_t* kv_empty = kv_full + G::NRINGS * STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(kv_empty + G::NRINGS * STAGES);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmKV);
+    for (int s = 0; s < SLOTS; ++s) {
+      mbar_init(&q_full[s], 1);
+      mbar_init(&s_full[s], 1);
+      mbar_init(&s_free[s], 4);
+      mbar_init(&p_full[s], 4);
+      mbar_init(&p_empty[s], 1);
+      mbar_init(&o_full[s], 1);
+      mbar_init(&o_free[s], 4);
+    }
+    for (int i = 0; i < G::NRINGS * STAGES; ++i) {
+      mbar_init(&kv_full[i], 1);
+      mbar_init(&kv_empty[i], SHARED ? SLOTS : 1);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 0) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  pdl_sync();   // the prologue above touched no global data; everything below reads the predecessor's output
+
+  const int slot = warp < SLOTS ? warp : (warp - SLOTS) >> 2;
+  const int nchunks = (p.seqlen + BK - 1) / BK;
+  const int sh_total = p.nseq * p.heads;
+  const int first = SHARED ? static_cast<int>(blockIdx.x) : static_cast<int>(blockIdx.x) * SLOTS + slot;
+  const int stride = SHARED ? static_cast<int>(gridDim.x) : static_cast<int>(gridDim.x) * SLOTS;
+  // item -> (sequence, head, query tile of this slot); false when the slot idles during this item
+  auto decode = [&](int item, int& seq, int& head, int& qtile) -> bool {
+    if (SHARED) {
+      const int g = item / sh_total, sh = item - g * sh_total;
+      seq = sh / p.heads;
+      head = sh - seq * p.heads;
+      const int t0 = g * p.qtiles / p.ngroups, t1 = (g + 1) * p.qtiles / p.ngroups;
+      qtile = t0 + slot;
+      return qtile < t1;
+    }
+    qtile = item % p.qtiles;
+    const int sh = item / p.qtiles;
+    head = sh % p.heads;
+    seq = sh / p.heads;
+    return true;
+  };
+  const uint32_t tslot = tmem + static_cast<uint32_t>(slot) * G::SLOT_COLS;
+
+  if (warp < SLOTS) {
+    reg_dec<56>();
+    if (lane == 0) {
+      // -------------------------------------------------------------------- driver of one slot: TMA + tcgen05.mma
+      constexpr bool BF = Cvt<T>::is_bf16;
+      constexpr uint32_t idesc_s = umma_idesc_f16(BF, BM, BK);                 // S: N = 64 keys, Q and K both K-major
+      constexpr uint32_t idesc_o = umma_idesc_f16(BF, BM, DH) | (1u << 16);    // O: B (= V) is MN-major
+      const int ring_id = SHARED ? 0 : slot;
+      uint8_t* ring = sRing + ring_id * STAGES * G::STAGE_BYTES;
+      uint64_t* rfull = kv_full + ring_id * STAGES;
+      uint64_t* rempty = kv_empty + ring_id * STAGES;
+      const bool loader = SHARED ? slot == 0 : true;
+      uint32_t n_s = 0, n_pv = 0, n_item = 0, kv_use = 0, kv_load = 0;
+      for (int item = first; item < p.nitems; item += stride) {
+        int seq, head, qtile;
+        const bool active = decode(item, seq, head, qtile);
+        const int row0 = seq * p.seqlen;
+        const int colq = head * DH, colk = p.C + head * DH, colv = 2 * p.C + head * DH;
+        uint8_t* qbuf = sQ + (slot * 2 + (n_item & 1)) * G::Q_BYTES;
+        if (active) {
+          mbar_arrive_expect_tx(&q_full[slot], G::Q_BYTES);
+          tma_load_2d(qbuf, &tmQ, &q_full[slot], colq, row0 + qtile * BM);
+        }
+        auto load_chunk = [&](int c) {
+          const int st = kv_load % STAGES;
+          mbar_wait(&rempty[st], ((kv_load / STAGES) & 1) ^ 1);
+          mbar_arrive_expect_tx(&rfull[st], G::STAGE_BYTES);
+          tma_load_2d(ring + st * G::STAGE_BYTES, &tmKV, &rfull[st], colk, row0 + c * BK);
+          tma_load_2d(ring + st * G::STAGE_BYTES + G::KV_BYTES, &tmKV, &rfull[st], colv, row0 + c * BK);
+          ++kv_load;
+        };
+        int next_load = 0;
+        if (loader)
+          for (; next_load < nchunks && next_load < STAGES - 1; ++next_load) load_chunk(next_load);
+        const uint64_t qdesc = desc(smem_u32(qbuf), SBO, LAYOUT);
+        auto issue_s = [&](uint32_t chunk_pos) {                     // S(next) from the K chunk at ring position chunk_pos
+          const int st = chunk_pos % STAGES;
+          mbar_wait(&rfull[st], (chunk_pos / STAGES) & 1);
+          if (!active) return;
+          if (n_s > 0) mbar_wait(&s_free[slot], (n_s - 1) & 1);      // the softmax warps pulled the previous S out of TMEM
+          tc_fence_after();
+          const uint64_t kdesc = desc(smem_u32(ring + st * G::STAGE_BYTES), SBO, LAYOUT);
+#pragma unroll
+          for (int kk = 0; kk < DH / 16; ++kk) umma_f16_ss(tslot + COL_S, qdesc + 2 * kk, kdesc + 2 * kk, idesc_s, kk != 0 ? 1u : 0u);
+          umma_commit(&s_full[slot]);
+          ++n_s;
+        };
+        if (active) mbar_wait(&q_full[slot], n_item & 1);
+        issue_s(kv_use);
+        for (int j = 0; j < nchunks; ++j) {
+          if (j + 1 < nchunks) issue_s(kv_use + 1);                  // S(j+1) runs while the softmax warps work on S(j)
+          const int st = kv_use % STAGES;
+          if (active) {
+            mbar_wait(&p_full[slot], n_pv & 1);                      // P(j) is in TMEM, O carries the current reference maximum
+            if (j == 0 && n_item > 0) mbar_wait(&o_free[slot], (n_item - 1) & 1);   // the previous item's O has been read out
+            tc_fence_after();
+            const uint64_t vdesc = desc(smem_u32(ring + st * G::STAGE_BYTES + G::KV_BYTES), SBO, LAYOUT);
+#pragma unroll
+            for (int kk = 0; kk < BK / 16; ++kk)                     // 16 keys per MMA: A advances 8 TMEM columns, B 16 rows
+              mma_ts(tslot + COL_O, tslot + COL_P + 8 * kk, vdesc + ((16 * PITCH) >> 4) * kk, idesc_o, (j | kk) != 0 ? 1u : 0u);
+            umma_commit(&p_empty[slot]);
+            umma_commit(&rempty[st]);
+            ++n_pv;
+          } else {
+            mbar_arrive(&rempty[st]);                                // an idle slot of a lock-step item still releases the stage
+          }
+          ++kv_use;
+          if (loader && next_load < nchunks) load_chunk(next_load++);
+        }
+        if (active) {
+          umma_commit(&o_full[slot]);
+          ++n_item;
+        }
+      }
+    }
+  } else {
+    reg_inc<112>();
+    // ---------------------------------------------------------------------- softmax / epilogue: one thread per query row
+    const int quarter = warp & 3;                                  // TMEM lane quarter this warp may access
+    const int r = quarter * 32 + lane;
+    const uint32_t tbase = tslot + (static_cast<uint32_t>(quarter * 32) << 16);
+    const float c = p.scale_log2;
+    const uint64_t c2 = pk2(c, c);
+    uint32_t n_c = 0, n_item = 0;
+    for (int item = first; item < p.nitems; item += stride) {
+      int seq, head, qtile;
+      if (!decode(item, seq, head, qtile)) continue;
+      float m_ref = -INFINITY;
+      uint64_t lsum2 = pk2(0.f, 0.f);
+      for (int j = 0; j < nchunks; ++j, ++n_c) {
+        float v[64];
+        mbar_wait(&s_full[slot], n_c & 1);
+        tc_fence_after();
+        __syncwarp();
+        ld_x32(tbase + COL_S, v);
+        ld_x32(tbase + COL_S + 32, v + 32);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s_free[slot]);                 // one elected arrival per warp
+        const int nvalid = min(BK, p.seqlen - j * BK);             // keys >= nvalid belong to the next sequence / are padding
+        float mchunk;
+        if (nvalid == BK) {
+          float mm[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+          for (int i = 0; i < 16; i += 2)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) mm[q] = fmaxf(mm[q], fmaxf(v[q * 16 + i], v[q * 16 + i + 1]));
+          mchunk = fmaxf(fmaxf(mm[0], mm[1]), fmaxf(mm[2], mm[3]));
+        } else {
+          mchunk = -INFINITY;
+#pragma unroll
+          for (int i = 0; i < 64; ++i)
+            if (i < nvalid) mchunk = fmaxf(mchunk, v[i]);
+        }
+        // lazy reference maximum: a row's decision only involves its own thread
+        const bool move = (mchunk - m_ref) * c > LAZY_LOG2;        // true at j = 0 (m_ref = -inf)
+        const float alpha = move ? ex2((m_ref - mchunk) * c) : 1.f;
+        if (move) m_ref = mchunk;
+        const float msc = m_ref * c;
+        if (move) lsum2 = fma2(lsum2, pk2(alpha, alpha), pk2(0.f, 0.f));
+        const uint64_t nm2 = pk2(-msc, -msc), mg2 = pk2(MAGIC - msc, MAGIC - msc);
+        uint32_t pk[32];
+        auto body = [&](auto tail_tag) {
+          constexpr bool TAIL = decltype(tail_tag)::value;
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            if (TAIL && g * 8 >= nvalid) {                          // uniform: nothing valid in this group of 8 keys
+#pragma unroll
+              for (int q = 0; q < 4; ++q) pk[g * 4 + q] = 0u;
+              continue;
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const int i = g * 4 + q;                              // pair index: keys 2i, 2i+1
+              const uint64_t s2 = pk2(v[2 * i], v[2 * i + 1]);
+              float e0, e1;
+              if ((PMASK >> (i & 7)) & 1u) {
+                exp2_poly_pair(s2, c2, mg2, nm2, e0, e1);
+              } else {
+                float a0, a1;
+                upk2(fma2(s2, c2, nm2), a0, a1);
+                e0 = ex2(a0);
+                e1 = ex2(a1);
+              }
+              if (TAIL) {
+                e0 = 2 * i < nvalid ? e0 : 0.f;
+                e1 = 2 * i + 1 < nvalid ? e1 : 0.f;
+              }
+              pk[i] = Cvt<T>::pack(e0, e1);
+              lsum2 = add2(lsum2, pk2(e0, e1));
+            }
+          }
+        };
+        if (nvalid == BK) body(std::false_type{});
+        else body(std::true_type{});
+        // only now wait for PV(j-1): its latency hides behind the exponentials above (P is single-buffered)
+        if (n_c > 0) mbar_wait(&p_empty[slot], (n_c - 1) & 1);
+        tc_fence_after();
+        if (j > 0 && __any_sync(0xffffffffu, move)) {               // rare after the first chunks: rescale this row of O
+#pragma unroll
+          for (int cc = 0; cc < DH / 16; ++cc) {
+            float o16[16];
+            uint32_t u16[16];
+            __syncwarp();
+            tmem_ld_x16(tbase + COL_O + cc * 16, o16);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) u16[i] = __float_as_uint(o16[i] * alpha);
+            st_x16(tbase + COL_O + cc * 16, u16);
+          }
+        }
+        __syncwarp();
+        st_x16(tbase + COL_P, pk);
+        st_x16(tbase + COL_P + 16, pk + 16);
+        st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_full[slot]);
+      }
+      // ---- O / l -> global
+      float l0, l1;
+      upk2(lsum2, l0, l1);
+      const float inv = 1.f / (l0 + l1);
+      mbar_wait(&o_full[slot], n_item & 1);
+      tc_fence_after();
+      const int qrow = qtile * BM + r;
+      T* dst = reinterpret_cast<T*>(p.o) + (static_cast<long long>(seq) * p.seqlen + qrow) * p.ldo + head * DH;
+      U8 ov[DH / 16];
+#pragma unroll
+      for (int cc = 0; cc < DH / 16; ++cc) {
+        float o16[16];
+        __syncwarp();
+        tmem_ld_x16(tbase + COL_O + cc * 16, o16);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 8; ++i) ov[cc].v[i] = Cvt<T>::pack(o16[2 * i] * inv, o16[2 * i + 1] * inv);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&o_free[slot]);
+      ++n_item;
+      if (qrow < p.seqlen) {
+#pragma unroll
+        for (int cc = 0; cc < DH / 16; ++cc) stg256(dst + cc * 16, ov[cc]);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
+template <typename T, int DH, bool SHARED, uint32_t PMASK>
+static int launch_m(const AttnArgs& a, int C, cudaStream_t st) {
+  using G = Geo<DH, SHARED>;
+  CUtensorMap tq, tkv;
+  std::string err;
+  const cuuint64_t dims[2] = {static_cast<cuuint64_t>(a.ldq), static_cast<cuuint64_t>(a.nseq) * a.seqlen};
+  const cuuint64_t strides[1] = {static_cast<cuuint64_t>(a.ldq) * 2};
+  const cuuint32_t boxq[2] = {DH, BM}, boxkv[2] = {DH, BK};
+  const int dt = Cvt<T>::is_bf16 ? DT_BF16 : DT_F16;
+  if (tma_encode(&tq, dt, 2, a.q, dims, strides, boxq, DH * 2, &err)) return -3;
+  if (tma_encode(&tkv, dt, 2, a.q, dims, strides, boxkv, DH * 2, &err)) return -3;
+  SlotArgs p;
+  p.o = a.o; p.ldo = a.ldo; p.seqlen = a.seqlen; p.nseq = a.nseq; p.heads = a.heads; p.scale_log2 = a.scale_log2; p.C = C;
+  p.qtiles = (a.seqlen + BM - 1) / BM;
+  p.ngroups = (p.qtiles + SLOTS - 1) / SLOTS;
+  const long long sh = static_cast<long long>(a.nseq) * a.heads;
+  const long long nitems = SHARED ? sh * p.ngroups : sh * p.qtiles;
+  if (nitems > 0x7fffffffLL / 2) return -2;
+  p.nitems = static_cast<int>(nitems);
+  // One CTA per SM (it allocates all 512 TMEM columns): more than half of the shared memory is requested so that a second
+  // CTA can never become resident and spin inside tcgen05.alloc.
+  const size_t smem = std::max<size_t>(G::SMEM, 116 * 1024);
+  if (int e = ensure_max_dyn_smem(reinterpret_cast<const void*>(attn_slots_kernel<T, DH, SHARED, PMASK>), 227 * 1024)) return e;
+  const long long ctas = SHARED ? nitems : (nitems + SLOTS - 1) / SLOTS;
+  const unsigned grid = static_cast<unsigned>(std::min<long long>(ctas, current_device_sms()));
+  launch_k(attn_slots_kernel<T, DH, SHARED, PMASK>, dim3(grid), dim3(THREADS), smem, st, tq, tkv, p);
+  return static_cast<int>(cudaGetLastError());
+}
+
+// Which pairs (index mod 8) take the polynomial exp2: 3 of 8 (see the header); LWB_SLOTS_PMASK overrides for A/B runs.
+#ifndef LWB_SLOTS_PMASK
+#define LWB_SLOTS_PMASK 0x49u
+#endif
+
+template <typename T, int DH>
+static int launch(const AttnArgs& a, int C, cudaStream_t st) {
+  if (a.seqlen <= BM) return launch_m<T, DH, false, LWB_SLOTS_PMASK>(a, C, st);
+  return launch_m<T, DH, true, LWB_SLOTS_PMASK>(a, C, st);
+}
+
+}  // namespace sl
+
+// Packed-qkv path for head dims 16 / 32: q, k, v are the column blocks [0,C), [C,2C), [2C,3C) of one 16-bit matrix.
+int attention_slots_launch(int dtype, const AttnArgs& a, int dh, int C, cudaStream_t st) {
+  if (dtype == DT_BF16) {
+    if (dh == 16) return sl::launch<__nv_bfloat16, 16>(a, C, st);
+    if (dh == 32) return sl::launch<__nv_bfloat16, 32>(a, C, st);
+  } else {
+    if (dh == 16) return sl::launch<__half, 16>(a, C, st);
+    if (dh == 32) return sl::launch<__half, 32>(a, C, st);
+  }
+  return -2;
+}
+
+}  // namespace lwb

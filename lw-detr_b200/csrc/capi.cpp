@@ -2,6 +2,7 @@
 #include "lwdetr_b200.h"
 
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 #include <stdint.h>
 
 #include <string>
@@ -181,6 +182,7 @@ int lwdetr_create(const lwdetr_config* cfg, int dtype, lwdetr_handle** out) {
     return fail("lwdetr_create: img_size % 64, vit_dim % 64 and hidden_dim % 128 must be 0");
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail("lwdetr_create: no CUDA device (there is no CPU fallback)");
+  if (cfg->num_classes < 1 || cfg->num_classes > 4096) return fail("lwdetr_create: num_classes must be in [1, 4096]");
   lwdetr_handle* h = new (std::nothrow) lwdetr_handle;
   if (!h) return fail("lwdetr_create: out of memory");
   h->eng = new (std::nothrow) lwb::Engine(*cfg, dtype);
@@ -208,10 +210,69 @@ int lwdetr_forward(lwdetr_handle* h, const void* images, int images_fp32, int B,
                    const lwdetr_aux_out* aux, const int32_t* topk_override, void* stream) {
   if (!h || !images) return fail("lwdetr_forward: null pointer");
   std::string err;
-  if (h->eng->forward(images, images_fp32, B, pred_logits, pred_boxes, aux, topk_override, static_cast<cudaStream_t>(stream), &err))
+  lwb::ForwardIn in;
+  in.images = images; in.kind = images_fp32 ? lwb::IN_F32_NCHW : lwb::IN_16_NCHW;
+  if (h->eng->forward(in, B, pred_logits, pred_boxes, aux, topk_override, static_cast<cudaStream_t>(stream), &err))
     return fail(err);
   return 0;
 }
+
+int lwdetr_forward_ex(lwdetr_handle* h, const lwdetr_input* input, int B, float* pred_logits, float* pred_boxes,
+                      const lwdetr_aux_out* aux, const int32_t* topk_override, void* stream) {
+  if (!h || !input || !input->images) return fail("lwdetr_forward_ex: null pointer");
+  if (input->format != LWDETR_IN_F32_NCHW && input->format != LWDETR_IN_16_NCHW && input->format != LWDETR_IN_U8_NHWC)
+    return fail("lwdetr_forward_ex: format must be LWDETR_IN_F32_NCHW, LWDETR_IN_16_NCHW or LWDETR_IN_U8_NHWC");
+  lwb::ForwardIn in;
+  in.images = input->images; in.kind = input->format; in.mask = input->padding_mask;
+  for (int c = 0; c < 3; ++c) {
+    in.mean[c] = input->mean[c]; in.stdv[c] = input->std[c];
+    if (input->format == LWDETR_IN_U8_NHWC && !(input->std[c] > 0.f)) return fail("lwdetr_forward_ex: std must be positive");
+  }
+  std::string err;
+  if (h->eng->forward(in, B, pred_logits, pred_boxes, aux, topk_override, static_cast<cudaStream_t>(stream), &err)) return fail(err);
+  return 0;
+}
+
+// One ncclBroadcast of the packed weight arena.  NCCL is not linked: the symbol is taken from the
+// libnccl the host process already loaded (torch's bundled libnccl.so.2) or dlopen'ed by soname.
+int lwdetr_broadcast_weights(lwdetr_handle* h, void* nccl_comm, int root, void* stream) {
+  if (!h || !nccl_comm) return fail("lwdetr_broadcast_weights: null pointer");
+  if (!h->eng->weights_loaded()) return fail("lwdetr_broadcast_weights: call lwdetr_load_weights on every rank first (it fixes the arena layout)");
+  typedef int (*PFN_bcast)(const void*, void*, size_t, int, int, void*, cudaStream_t);
+  static PFN_bcast fn = nullptr;
+  if (!fn) {
+    void* sym = dlsym(RTLD_DEFAULT, "ncclBroadcast");
+    if (!sym) {
+      void* lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+      if (lib) sym = dlsym(lib, "ncclBroadcast");
+    }
+    if (!sym) return fail("lwdetr_broadcast_weights: ncclBroadcast not found (load libnccl.so.2 into the process first)");
+    fn = reinterpret_cast<PFN_bcast>(sym);
+  }
+  int prev = 0;
+  cudaGetDevice(&prev);
+  cudaSetDevice(h->eng->device());
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  // layout check: every rank must hold an arena of the root's size (same config, dtype and library version)
+  unsigned long long* dsz = nullptr;
+  unsigned long long mine = h->eng->arena_used(), roots = 0;
+  int rc = 0;
+  if (cudaMalloc(&dsz, 8) != cudaSuccess) rc = -1;
+  if (!rc && cudaMemcpyAsync(dsz, &mine, 8, cudaMemcpyHostToDevice, st) != cudaSuccess) rc = -1;
+  if (!rc && fn(dsz, dsz, 8, /*ncclChar*/ 0, root, nccl_comm, st) != 0) rc = -2;
+  if (!rc && cudaMemcpyAsync(&roots, dsz, 8, cudaMemcpyDeviceToHost, st) != cudaSuccess) rc = -1;
+  if (!rc && cudaStreamSynchronize(st) != cudaSuccess) rc = -1;
+  if (dsz) cudaFree(dsz);
+  if (!rc && roots != mine) rc = -3;
+  if (!rc && fn(h->eng->arena_ptr(), h->eng->arena_ptr(), h->eng->arena_used(), 0, root, nccl_comm, st) != 0) rc = -2;
+  cudaSetDevice(prev);
+  if (rc == -1) return fail(std::string("lwdetr_broadcast_weights: CUDA error: ") + cudaGetErrorString(cudaGetLastError()));
+  if (rc == -2) return fail("lwdetr_broadcast_weights: ncclBroadcast failed");
+  if (rc == -3) return fail("lwdetr_broadcast_weights: arena size differs from the root's (" + std::to_string(mine) + " vs " + std::to_string(roots) + " bytes): config / dtype mismatch between ranks");
+  return 0;
+}
+
+int64_t lwdetr_weight_arena_bytes(lwdetr_handle* h) { return h ? static_cast<int64_t>(h->eng->arena_used()) : -1; }
 
 int lwdetr_set_option(lwdetr_handle* h, const char* name, int value) {
   if (!h || !name) return fail("lwdetr_set_option: null pointer");

@@ -67,7 +67,19 @@ void bicubic_resize_chlast(const float* src, int n_in, int C, int n_out, float* 
 }
 
 // ------------------------------------------------------------------------------- Engine basics
-Engine::Engine(const lwdetr_config& cfg, int dtype) : cfg_(cfg), dtype_(dtype) {}
+Engine::Engine(const lwdetr_config& cfg, int dtype) : cfg_(cfg), dtype_(dtype) { cudaGetDevice(&device_); }
+
+namespace {
+// Switches to the engine's device for the duration of a call (the caller's current device is restored afterwards).
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    if (prev != dev) cudaSetDevice(dev); else prev = -1;
+  }
+  ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+}  // namespace
 
 void Engine::drop_graphs() {
   for (auto& kv : graphs_) cudaGraphExecDestroy(kv.second);
@@ -75,6 +87,7 @@ void Engine::drop_graphs() {
 }
 
 Engine::~Engine() {
+  DeviceGuard guard(device_);
   drop_graphs();
   if (gstream_) cudaStreamDestroy(gstream_);
   if (ev_in_) cudaEventDestroy(ev_in_);
@@ -144,6 +157,11 @@ int Engine::set_option(const char* name, int value) {
 
 // ------------------------------------------------------------------------------- weight packing
 int Engine::load_weights(const std::map<std::string, HostTensor>& w, std::string* err) {
+  DeviceGuard guard(device_);
+  // Whatever happens below, the old packing is gone: a failed load must not leave a schedule pointing into a freed arena.
+  weights_loaded_ = false;
+  planned_B_ = 0;
+  ops_.clear();
   const int C = cfg_.vit_dim, d = cfg_.hidden_dim, nq = cfg_.num_queries, ncls = cfg_.num_classes;
   const int G = cfg_.img_size / 16, T = G * G, ntap = cfg_.n_taps, c2 = d / 2;
   const int M = cfg_.ca_heads, L = cfg_.n_levels, P = cfg_.dec_points, ff = cfg_.dim_feedforward;
@@ -363,28 +381,6 @@ int Engine::load_weights(const std::map<std::string, HostTensor>& w, std::string
   put_norm("dec_norm", TR + "decoder.norm", d);
   put_linear("cls", "class_embed", ncls, d);
   for (int i = 0; i < 3; ++i) put_linear("box" + std::to_string(i), "bbox_embed.layers." + std::to_string(i), i == 2 ? 4 : d, d);
-  // ---- proposals (transformer.py:71-125, no padding, unsigmoid=False) and the rows they invalidate
-  {
-    std::vector<float> prop;
-    invalid_rows_.clear();
-    for (int l = 0; l < L; ++l) {
-      const int sc = cfg_.level_scale_log2[l];
-      const int H = sc == 1 ? 2 * G : (sc == -1 ? G / 2 : G);
-      const float whv = 0.05f * std::pow(2.0f, static_cast<float>(l));
-      for (int y = 0; y < H; ++y)
-        for (int x = 0; x < H; ++x) {
-          const float v[4] = {(x + 0.5f) / H, (y + 0.5f) / H, whv, whv};
-          bool ok = true;
-          for (float f : v) ok = ok && (f > 0.01f) && (f < 0.99f);
-          for (float f : v) prop.push_back(ok ? f : 0.f);
-          invalid_rows_.push_back(ok ? 0 : 1);
-        }
-    }
-    put32("proposals", prop);
-    void* fl = walloc(invalid_rows_.size());
-    if (!fl) oom = true; else cudaMemcpy(fl, invalid_rows_.data(), invalid_rows_.size(), cudaMemcpyHostToDevice);
-    W_["invalid"] = fl;
-  }
   if (missing) return -1;
   if (oom) { *err = "weight arena exhausted"; return -1; }
   if (cudaDeviceSynchronize() != cudaSuccess) { *err = "CUDA error while uploading weights"; return -1; }
@@ -499,6 +495,20 @@ int Engine::plan(int B, std::string* err) {
     };
     const int dt = dtype_;
 
+    // ================================================================ padding-mask tables (constants when the batch is unpadded)
+    float* prop_b = buf32(BS * 4);
+    float* vr_b = buf32(static_cast<long long>(B) * L * 2 + 4);
+    uint8_t* invalid_b = static_cast<uint8_t*>(salloc(static_cast<size_t>(BS)));
+    uint8_t* pad_b = static_cast<uint8_t*>(salloc(static_cast<size_t>(BS)));
+    {
+      const int img = cfg_.img_size;
+      const int lh0 = lvl_hw[0], lh1 = lvl_hw[1], ls0 = lvl_start[0], ls1 = lvl_start[1];
+      add_op("mask_setup", [this, B, img, L, S, lh0, lh1, ls0, ls1, prop_b, invalid_b, pad_b, vr_b](cudaStream_t st) {
+        const int lh[2] = {lh0, lh1}, ls[2] = {ls0, ls1};
+        return mask_setup_launch(in_.mask, B, img, img, L, S, lh, lh, ls, prop_b, invalid_b, pad_b, vr_b, st);
+      }, prop_b, BS, 4, 4, 1, 24.0 * BS);
+      if (pass) ops_.back().reads_input = true;
+    }
     // ================================================================ ViT encoder
     Mat a0 = buf16(BT, 768);
     Mat xa = buf16(BT, C), xb = buf16(BT, C), xm = buf16(BT, C), lnb = buf16(BT, C);
@@ -507,8 +517,12 @@ int Engine::plan(int B, std::string* err) {
     {
       void* a0p = a0.p;
       const int img = cfg_.img_size;
-      add_op("patch_gather", [this, a0p, B, img, dt](cudaStream_t st) { return patch_gather_launch(dt, in_images_, in_images_fp32_, a0p, B, img, st); },
+      add_op("patch_gather", [this, a0p, B, img, dt](cudaStream_t st) {
+               if (in_.kind == IN_U8_NHWC) return patch_gather_u8_launch(dt, in_.images, in_.mean, in_.stdv, a0p, B, img, st);
+               return patch_gather_launch(dt, in_.images, in_.kind == IN_F32_NCHW ? 1 : 0, a0p, B, img, st);
+             },
              a0.p, BT, 768, 768, 0, 1.0 * B * 3 * img * img * 4 + 2.0 * BT * 768);
+      if (pass) ops_.back().reads_input = true;
     }
     float2* stats_x = static_cast<float2*>(salloc(static_cast<size_t>(BT) * 48 * sizeof(float2)));   // row stats of x (block input)
     float2* stats_m = static_cast<float2*>(salloc(static_cast<size_t>(BT) * 48 * sizeof(float2)));   // row stats of x + attn
@@ -617,10 +631,9 @@ int Engine::plan(int B, std::string* err) {
     float* enc_boxes = buf32(BQ * 4);
     float* refpoint = buf32(BQ * 4);
     Mat sine = buf16(BQ, 2 * d), qpos = buf16(BQ, d);
-    { GemmOpt o; o.hm_S = S; o.hm_heads = M; o.hm_slices = NL; add_gemm("value_proj", memory, BS, d, "value", NL * d, value.p, 16, o, BS * NL * M); }
+    { GemmOpt o; o.hm_S = S; o.hm_heads = M; o.hm_slices = NL; o.row_zero = pad_b; add_gemm("value_proj", memory, BS, d, "value", NL * d, value.p, 16, o, BS * NL * M); }
     add_gemm("enc_output", memory, BS, d, "enc_out", d, om.p, om.ld, GemmOpt{});
-    add_ln("enc_output_norm", om, omn, "enc_ln", 1e-5f, BS, d, pass ? static_cast<const uint8_t*>(w16("invalid")) : nullptr, S,
-           pass ? w32("enc_out.b") : nullptr);
+    add_ln("enc_output_norm", om, omn, "enc_ln", 1e-5f, BS, d, invalid_b, static_cast<int>(BS), pass ? w32("enc_out.b") : nullptr);
     { GemmOpt o; o.out_fp32 = 1; add_gemm("enc_class", omn, BS, d, "enc_cls", ncls, cls_all, ldc, o); }
     add_op("enc_score", [cls_all, ncls, ldc, score, BS](cudaStream_t st) { return rowmax_launch(cls_all, ldc, ncls, score, BS, st); }, score, BS, 1, 1, 1, 4.0 * BS * ncls);
     add_op("topk", [this, score, B, S, nq, topk_idx](cudaStream_t st) {
@@ -638,10 +651,10 @@ int Engine::plan(int B, std::string* err) {
     { GemmOpt o; o.act = ACT_RELU; add_gemm("enc_box1", h1, BQ, d, "enc_box1", d, h2.p, h2.ld, o); }
     { GemmOpt o; o.out_fp32 = 1; add_gemm("enc_box2", h2, BQ, d, "enc_box2", 4, delta_ts, 4, o); }
     {
-      const float* prop = pass ? w32("proposals") : nullptr; const float* rpe = pass ? w32("refpoint_embed") : nullptr;
+      const float* rpe = pass ? w32("refpoint_embed") : nullptr;
       void* sp = sine.p;
-      add_op("query_init", [delta_ts, prop, topk_idx, rpe, B, nq, d, enc_boxes, refpoint, sp, dt](cudaStream_t st) {
-        return query_init_launch(dt, delta_ts, prop, topk_idx, rpe, B, nq, d, enc_boxes, refpoint, sp, st);
+      add_op("query_init", [delta_ts, prop_b, topk_idx, rpe, B, nq, d, enc_boxes, refpoint, sp, dt, S, L, vr_b](cudaStream_t st) {
+        return query_init_launch(dt, delta_ts, prop_b, topk_idx, rpe, B, nq, d, enc_boxes, refpoint, sp, S, L, vr_b, st);
       }, refpoint, BQ, 4, 4, 1, 4.0 * BQ * d);
     }
     { GemmOpt o; o.act = ACT_RELU; add_gemm("ref_point_head0", sine, BQ, 2 * d, "rph0", d, h1.p, h1.ld, o); }
@@ -658,7 +671,7 @@ int Engine::plan(int B, std::string* err) {
     }
     MsdaArgs mbase;
     std::memset(&mbase, 0, sizeof mbase);
-    mbase.v_b_stride = 1LL * NL * M * S * MSDA_D; mbase.offs_logits = oa.p; mbase.ld_ol = oa.ld; mbase.ref = refpoint; mbase.out = ms.p; mbase.ld_out = ms.ld;
+    mbase.v_b_stride = 1LL * NL * M * S * MSDA_D; mbase.valid_ratio = vr_b; mbase.offs_logits = oa.p; mbase.ld_ol = oa.ld; mbase.ref = refpoint; mbase.out = ms.p; mbase.ld_out = ms.ld;
     mbase.batch = B; mbase.nq = nq; mbase.heads = M; mbase.levels = L; mbase.points = P; mbase.S = S;
     for (int l = 0; l < L; ++l) { mbase.lvl_h[l] = lvl_hw[l]; mbase.lvl_w[l] = lvl_hw[l]; mbase.lvl_start[l] = lvl_start[l]; }
     if (msda_plan(&mbase)) { *err = "deformable attention: a feature level is too wide to stage"; return -1; }
@@ -734,12 +747,14 @@ int Engine::do_capture(const Op& op, cudaStream_t st) {
   return 0;
 }
 
-int Engine::forward(const void* images, int images_fp32, int B, float* pred_logits, float* pred_boxes, const lwdetr_aux_out* aux,
+int Engine::forward(const ForwardIn& in, int B, float* pred_logits, float* pred_boxes, const lwdetr_aux_out* aux,
                     const int32_t* topk_override, cudaStream_t st, std::string* err) {
+  DeviceGuard guard(device_);
   if (!weights_loaded_) { *err = "lwdetr_forward: weights not loaded"; return -1; }
   if (B <= 0) { *err = "lwdetr_forward: batch must be positive"; return -1; }
   if (B != planned_B_ && plan(B, err)) return -1;
-  in_images_ = images; in_images_fp32_ = images_fp32; in_topk_override_ = topk_override;
+  if (!in.images) { *err = "lwdetr_forward: null images"; return -1; }
+  in_ = in; in_topk_override_ = topk_override;
   // The first forward of a plan always runs eagerly (it also performs the one-time cudaFuncSetAttribute calls).
   const bool graph_ok = use_graph_ && captures_.empty() && eager_runs_ > 0;
   if (graph_ok) {
@@ -748,14 +763,14 @@ int Engine::forward(const void* images, int images_fp32, int B, float* pred_logi
           cudaEventCreateWithFlags(&ev_in_, cudaEventDisableTiming) != cudaSuccess ||
           cudaEventCreateWithFlags(&ev_out_, cudaEventDisableTiming) != cudaSuccess) { *err = "graph stream setup failed"; return -1; }
     }
-    const GraphKey key{images, images_fp32, topk_override};
+    const GraphKey key{topk_override};
     auto it = graphs_.find(key);
     if (it == graphs_.end()) {
       if (graphs_.size() >= 8) drop_graphs();
       cudaGraph_t g = nullptr;
       if (cudaStreamBeginCapture(gstream_, cudaStreamCaptureModeThreadLocal) != cudaSuccess) { *err = std::string("graph capture begin failed: ") + cudaGetErrorString(cudaGetLastError()); return -1; }
       int rc = 0;
-      for (auto& op : ops_) { rc = op.run(gstream_); if (rc) break; }
+      for (auto& op : ops_) { if (op.reads_input) continue; rc = op.run(gstream_); if (rc) break; }
       cudaError_t ce = cudaStreamEndCapture(gstream_, &g);
       if (rc || ce != cudaSuccess) { if (g) cudaGraphDestroy(g); *err = "graph capture failed"; return -1; }
       cudaGraphExec_t ex = nullptr;
@@ -763,7 +778,12 @@ int Engine::forward(const void* images, int images_fp32, int B, float* pred_logi
       cudaGraphDestroy(g);
       it = graphs_.emplace(key, ex).first;
     }
-    // order the graph after the caller's stream and the caller's stream after the graph
+    // the input-reading ops on the caller's stream, then the graph ordered after them, then the caller's stream after the graph
+    for (auto& op : ops_) {
+      if (!op.reads_input) continue;
+      const int rc = op.run(st);
+      if (rc) { *err = "op " + op.label + " failed to launch"; return -1; }
+    }
     if (cudaEventRecord(ev_in_, st) != cudaSuccess || cudaStreamWaitEvent(gstream_, ev_in_, 0) != cudaSuccess ||
         cudaGraphLaunch(it->second, gstream_) != cudaSuccess || cudaEventRecord(ev_out_, gstream_) != cudaSuccess ||
         cudaStreamWaitEvent(st, ev_out_, 0) != cudaSuccess) { *err = std::string("graph launch failed: ") + cudaGetErrorString(cudaGetLastError()); return -1; }
@@ -798,6 +818,7 @@ int Engine::forward(const void* images, int images_fp32, int B, float* pred_logi
 }
 
 int Engine::profile_ops(int iters, std::vector<float>* ms, cudaStream_t st, std::string* err) {
+  DeviceGuard guard(device_);
   if (planned_B_ <= 0) { *err = "profile_ops: run a forward first"; return -1; }
   ms->assign(ops_.size(), 0.f);
   cudaEvent_t e0, e1;

@@ -168,6 +168,123 @@ int patch_gather_launch(int dtype, const void* img, int img_is_fp32, void* A, in
   return static_cast<int>(cudaGetLastError());
 }
 
+// uint8 HWC image [B, S, S, 3] (what an image decoder + resize produce; demo/demo.py:146-159 then runs ToTensor -> /255 and
+// Normalize(mean, std), datasets/transforms.py:223-252) -> the same 16-bit patch matrix.  The normalisation is fused
+// into the gather: the fp32 NCHW image of the reference (4.9 MB per image) never exists.  One thread = the 16 pixels
+// of one patch row, all three channels: three 16-byte loads, three 32-byte stores.
+struct NormParams {
+  float mean[3], stdv[3];
+};
+template <typename T>
+__global__ void __launch_bounds__(256) patch_gather_u8_kernel(const uint8_t* __restrict__ img, T* __restrict__ A, int B, int S, const NormParams np) {
+  pdl_sync();
+  const int G = S / 16, T_ = G * G;
+  const long long rows = static_cast<long long>(B) * T_;
+  const long long id = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;      // (py, row): row fastest
+  if (id >= rows * 16) return;
+  const long long r = id % rows;
+  const int py = static_cast<int>(id / rows);
+  const int b = static_cast<int>(r / T_), rem = static_cast<int>(r % T_);
+  const int wh = G / 4, wsz = wh * wh;
+  const int win = rem / wsz, t = rem % wsz;
+  const int Y = (win >> 2) * wh + t / wh, X = (win & 3) * wh + t % wh;
+  const uint8_t* src = img + ((static_cast<long long>(b) * S + (Y * 16 + py)) * S + X * 16) * 3;
+  uint32_t w[12];
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    const uint4 q = __ldg(reinterpret_cast<const uint4*>(src) + j);
+    w[4 * j] = q.x; w[4 * j + 1] = q.y; w[4 * j + 2] = q.z; w[4 * j + 3] = q.w;
+  }
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    float f[16];
+#pragma unroll
+    for (int px = 0; px < 16; ++px) {
+      const int byte = px * 3 + c;
+      const float u = static_cast<float>((w[byte >> 2] >> ((byte & 3) * 8)) & 0xffu);
+      f[px] = (u / 255.f - np.mean[c]) / np.stdv[c];             // ToTensor (/255) then Normalize, IEEE divisions as torch
+    }
+    U8 o;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o.v[j] = Cvt<T>::pack(f[2 * j], f[2 * j + 1]);
+    stg256(A + r * 768 + c * 256 + py * 16, o);
+  }
+}
+
+int patch_gather_u8_launch(int dtype, const void* img, const float* mean, const float* stdv, void* A, int B, int S, cudaStream_t st) {
+  if (S % 64 != 0) return -2;
+  NormParams np;
+  for (int c = 0; c < 3; ++c) { np.mean[c] = mean[c]; np.stdv[c] = stdv[c]; }
+  const long long total = static_cast<long long>(B) * (S / 16) * (S / 16) * 16;
+  const unsigned grid = static_cast<unsigned>((total + 255) / 256);
+  if (dtype == DT_BF16) launch_k(patch_gather_u8_kernel<__nv_bfloat16>, dim3(grid), dim3(256), 0, st, static_cast<const uint8_t*>(img), static_cast<__nv_bfloat16*>(A), B, S, np);
+  else launch_k(patch_gather_u8_kernel<__half>, dim3(grid), dim3(256), 0, st, static_cast<const uint8_t*>(img), static_cast<__half*>(A), B, S, np);
+  return static_cast<int>(cudaGetLastError());
+}
+
+// ----------------------------------------------------------------------------------- padding-mask tables (padded / mixed-size batches)
+// From the NestedTensor mask [B, Himg, Wimg] (True = padded pixel, util/misc.py:317-339) build, per image and level:
+//   the level mask by nearest resize (backbone.py:153-158), valid_H / valid_W and the valid ratios (transformer.py:
+//   189-196), the encoder proposals ((j+.5)/valid_W, (i+.5)/valid_H, .05*2^lvl, .05*2^lvl), the rows whose memory /
+//   proposal are zeroed (padding or a component outside (0.01, 0.99); transformer.py:71-125) and the rows whose VALUE is
+//   zeroed (padding only; ms_deform_attn.py:114-115).  mask == nullptr means "no padding": the tables then equal the
+//   per-config constants.  One CTA per (image, level).
+struct MaskSetupArgs {
+  const uint8_t* mask;
+  int B, Himg, Wimg, L, S;
+  int lvl_h[4], lvl_w[4], lvl_start[4];
+  float* proposals;    // [B, S, 4]
+  uint8_t* invalid;    // [B, S]
+  uint8_t* pad;        // [B, S]
+  float* valid_ratio;  // [B, L, 2] (w, h)
+};
+__global__ void __launch_bounds__(256) mask_setup_kernel(const MaskSetupArgs p) {
+  pdl_sync();
+  const int b = blockIdx.x / p.L, l = blockIdx.x % p.L;
+  const int H = p.lvl_h[l], W = p.lvl_w[l];
+  const float sy = static_cast<float>(p.Himg) / H, sx = static_cast<float>(p.Wimg) / W;     // F.interpolate(mode="nearest") source index
+  auto padded = [&](int i, int j) -> bool {
+    if (p.mask == nullptr) return false;
+    const int yi = min(static_cast<int>(floorf(i * sy)), p.Himg - 1), xi = min(static_cast<int>(floorf(j * sx)), p.Wimg - 1);
+    return p.mask[(static_cast<long long>(b) * p.Himg + yi) * p.Wimg + xi] != 0;
+  };
+  __shared__ int vh, vw;
+  if (threadIdx.x == 0) { vh = 0; vw = 0; }
+  __syncthreads();
+  for (int i = threadIdx.x; i < H; i += blockDim.x) if (!padded(i, 0)) atomicAdd(&vh, 1);     // transformer.py:87-88
+  for (int j = threadIdx.x; j < W; j += blockDim.x) if (!padded(0, j)) atomicAdd(&vw, 1);
+  __syncthreads();
+  const float valid_h = static_cast<float>(vh), valid_w = static_cast<float>(vw);
+  if (threadIdx.x == 0) {
+    p.valid_ratio[(b * p.L + l) * 2] = valid_w / W;                                           // transformer.py:189-196
+    p.valid_ratio[(b * p.L + l) * 2 + 1] = valid_h / H;
+  }
+  const float whv = 0.05f * exp2f(static_cast<float>(l));
+  for (int t = threadIdx.x; t < H * W; t += blockDim.x) {
+    const int i = t / W, j = t - i * W;
+    const bool pd = padded(i, j);
+    const float v[4] = {(j + 0.5f) / valid_w, (i + 0.5f) / valid_h, whv, whv};
+    bool ok = true;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) ok = ok && (v[c] > 0.01f) && (v[c] < 0.99f);
+    const long long row = static_cast<long long>(b) * p.S + p.lvl_start[l] + t;
+    const bool keep = ok && !pd;
+    reinterpret_cast<float4*>(p.proposals)[row] = keep ? make_float4(v[0], v[1], v[2], v[3]) : make_float4(0.f, 0.f, 0.f, 0.f);
+    p.invalid[row] = keep ? 0 : 1;
+    p.pad[row] = pd ? 1 : 0;
+  }
+}
+int mask_setup_launch(const uint8_t* mask, int B, int Himg, int Wimg, int L, int S, const int* lvl_h, const int* lvl_w, const int* lvl_start,
+                      float* proposals, uint8_t* invalid, uint8_t* pad, float* valid_ratio, cudaStream_t st) {
+  if (L < 1 || L > 4) return -2;
+  MaskSetupArgs a;
+  a.mask = mask; a.B = B; a.Himg = Himg; a.Wimg = Wimg; a.L = L; a.S = S;
+  for (int l = 0; l < 4; ++l) { a.lvl_h[l] = l < L ? lvl_h[l] : 0; a.lvl_w[l] = l < L ? lvl_w[l] : 0; a.lvl_start[l] = l < L ? lvl_start[l] : 0; }
+  a.proposals = proposals; a.invalid = invalid; a.pad = pad; a.valid_ratio = valid_ratio;
+  launch_k(mask_setup_kernel, dim3(static_cast<unsigned>(B * L)), dim3(256), 0, st, a);
+  return static_cast<int>(cudaGetLastError());
+}
+
 // ----------------------------------------------------------------------------------- window-major -> spatial copy
 template <typename T>
 __global__ void __launch_bounds__(256) unwindow_kernel(const T* __restrict__ src, int lds, T* __restrict__ dst, int ldd,
@@ -328,7 +445,8 @@ template <typename T>
 __global__ void __launch_bounds__(256) query_init_kernel(const float* __restrict__ delta_ts, const float* __restrict__ proposals,
                                                          const int* __restrict__ idx, const float* __restrict__ refpoint_embed,
                                                          int k, int d, long long rows, float* __restrict__ box_ts,
-                                                         float* __restrict__ refpoint, T* __restrict__ sine) {
+                                                         float* __restrict__ refpoint, T* __restrict__ sine, int S, int L,
+                                                         const float* __restrict__ valid_ratio) {
   pdl_sync();   // programmatic dependent launch: release the successor, wait for the predecessor (launch.h)
   const long long row = blockIdx.x;
   if (row >= rows) return;
@@ -336,7 +454,7 @@ __global__ void __launch_bounds__(256) query_init_kernel(const float* __restrict
   __shared__ float rp[4];
   if (threadIdx.x < 4) {
     const int c = threadIdx.x;
-    const float* pr = proposals + static_cast<long long>(idx[row]) * 4;
+    const float* pr = proposals + (static_cast<long long>(row / k) * S + idx[row]) * 4;       // per-image proposal table [B, S, 4]
     const float* dl = delta_ts + row * 4;
     const float bx = c < 2 ? dl[c] * pr[c + 2] + pr[c] : expf(dl[c]) * pr[c];
     box_ts[row * 4 + c] = bx;
@@ -346,7 +464,8 @@ __global__ void __launch_bounds__(256) query_init_kernel(const float* __restrict
     const float e = refpoint_embed[j * 4 + c];
     const float r = c < 2 ? e * bwh + bxy : expf(e) * bwh;
     refpoint[row * 4 + c] = r;
-    rp[c] = r;
+    // the sine embedding sees the level-0 reference box scaled by the valid ratio (transformer.py:352-355; 1 when unpadded)
+    rp[c] = r * valid_ratio[(row / k) * L * 2 + (c & 1)];
   }
   __syncthreads();
   const int dim = d / 2;                        // per-coordinate embedding width
@@ -361,10 +480,10 @@ __global__ void __launch_bounds__(256) query_init_kernel(const float* __restrict
   }
 }
 int query_init_launch(int dtype, const float* delta_ts, const float* proposals, const int* idx, const float* refpoint_embed, int B,
-                      int k, int d, float* box_ts, float* refpoint, void* sine, cudaStream_t st) {
+                      int k, int d, float* box_ts, float* refpoint, void* sine, int S, int L, const float* valid_ratio, cudaStream_t st) {
   const long long rows = static_cast<long long>(B) * k;
-  if (dtype == DT_BF16) launch_k(query_init_kernel<__nv_bfloat16>, dim3(static_cast<unsigned>(rows)), dim3(256), 0, st, delta_ts, proposals, idx, refpoint_embed, k, d, rows, box_ts, refpoint, static_cast<__nv_bfloat16*>(sine));
-  else launch_k(query_init_kernel<__half>, dim3(static_cast<unsigned>(rows)), dim3(256), 0, st, delta_ts, proposals, idx, refpoint_embed, k, d, rows, box_ts, refpoint, static_cast<__half*>(sine));
+  if (dtype == DT_BF16) launch_k(query_init_kernel<__nv_bfloat16>, dim3(static_cast<unsigned>(rows)), dim3(256), 0, st, delta_ts, proposals, idx, refpoint_embed, k, d, rows, box_ts, refpoint, static_cast<__nv_bfloat16*>(sine), S, L, valid_ratio);
+  else launch_k(query_init_kernel<__half>, dim3(static_cast<unsigned>(rows)), dim3(256), 0, st, delta_ts, proposals, idx, refpoint_embed, k, d, rows, box_ts, refpoint, static_cast<__half*>(sine), S, L, valid_ratio);
   return static_cast<int>(cudaGetLastError());
 }
 

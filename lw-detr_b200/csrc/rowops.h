@@ -19,6 +19,11 @@ struct LayerNormArgs {
 int layernorm_launch(int dtype, const LayerNormArgs& a, cudaStream_t st);
 
 int patch_gather_launch(int dtype, const void* img, int img_is_fp32, void* A, int B, int S, cudaStream_t st);
+// uint8 HWC [B,S,S,3] with fused (x/255 - mean) / std
+int patch_gather_u8_launch(int dtype, const void* img, const float* mean, const float* stdv, void* A, int B, int S, cudaStream_t st);
+// padding-mask tables of a (possibly) padded batch; mask == nullptr: no padding
+int mask_setup_launch(const uint8_t* mask, int B, int Himg, int Wimg, int L, int S, const int* lvl_h, const int* lvl_w, const int* lvl_start,
+                      float* proposals, uint8_t* invalid, uint8_t* pad, float* valid_ratio, cudaStream_t st);
 int unwindow_launch(int dtype, const void* src, int lds, void* dst, int ldd, long long rows, int C, int G, cudaStream_t st);
 int add_rows_launch(int dtype, const void* a, int lda, long long amod, const void* b, int ldb, void* out, int ldo,
                     long long rows, int C, cudaStream_t st);
@@ -30,7 +35,7 @@ int postprocess_launch(const float* logits, const float* boxes, const float* tar
 int gather_topk_launch(int dtype, const void* feat, int ldf, const float* logits, int ldl, int ncls, const int* idx, int B, int S,
                        int k, int d, void* sel, float* enc_logits, cudaStream_t st);
 int query_init_launch(int dtype, const float* delta_ts, const float* proposals, const int* idx, const float* refpoint_embed, int B,
-                      int k, int d, float* box_ts, float* refpoint, void* sine, cudaStream_t st);
+                      int k, int d, float* box_ts, float* refpoint, void* sine, int S, int L, const float* valid_ratio, cudaStream_t st);
 int final_boxes_launch(const float* delta, const float* refpoint, long long rows_per_layer, int layers, float* boxes, cudaStream_t st);
 
 }  // namespace lwb

@@ -61,10 +61,11 @@ class LWDETR(nn.Module):
         if self._engine is not None and self._engine.dtype == dt and (self.assume_frozen and self._engine_sig is not None):
             return self._engine
         sig = (self._weights_signature(), dt)
-        if self._engine is None or self._engine.dtype != dt:
+        pdev = next(self.parameters()).device
+        if self._engine is None or self._engine.dtype != dt or (pdev.type == "cuda" and self._engine.device != pdev):
             if self._engine is not None:
                 self._engine.close()
-            self._engine = capi.Engine(self.cfg, dt)
+            self._engine = capi.Engine(self.cfg, dt, device=next(self.parameters()).device)
             self._engine_sig = None
         if self._engine_sig != sig:
             self._engine.load_state_dict(self.state_dict())
@@ -103,14 +104,24 @@ class LWDETR(nn.Module):
         if isinstance(samples, (list, torch.Tensor)):
             samples = nested_tensor_from_tensor_list(samples)
         x, mask = samples.tensors, samples.mask
-        if mask is not None and bool(mask.any()):
-            raise NotImplementedError("lwdetr_b200 v1 handles same-size, unpadded batches (all released eval scripts "
-                                      "use --square_resize_div_64, scripts/*_eval.sh:27-28)")
         dev = next(self.parameters()).device
         if dev.type != "cuda":
             raise RuntimeError("lwdetr_b200: move the model to a CUDA device (no CPU fallback)")
+        S = self.cfg.img_size
+        if x.dim() != 4 or x.shape[-1] > S or x.shape[-2] > S:
+            raise RuntimeError("lwdetr_b200: images larger than the configured %dx%d are not supported, got %s" % (S, S, tuple(x.shape)))
+        if x.shape[-1] != S or x.shape[-2] != S:
+            # a batch whose largest image is smaller than the model's input: pad to the configured size (bottom / right,
+            # exactly what nested_tensor_from_tensor_list does between the images of a batch) and extend the mask
+            xp = x.new_zeros((x.shape[0], x.shape[1], S, S))
+            xp[:, :, : x.shape[-2], : x.shape[-1]] = x
+            mp = torch.ones((x.shape[0], S, S), dtype=torch.bool, device=x.device)
+            mp[:, : x.shape[-2], : x.shape[-1]] = mask if mask is not None else False
+            x, mask = xp, mp
         x = x.to(dev)
-        out = self.engine().forward(x, want_aux=True)
+        # the padding mask only matters when something IS padded (misc.py:317-339); an all-False mask takes the constant tables
+        mask = mask.to(dev) if (mask is not None and bool(mask.any())) else None
+        out = self.engine().forward(x, want_aux=True, mask=mask)
         if self._export:
             return out["pred_boxes"], out["pred_logits"]      # forward_export tuple (lwdetr.py:176-195)
         res = {"pred_logits": out["pred_logits"], "pred_boxes": out["pred_boxes"]}

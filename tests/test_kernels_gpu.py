@@ -28,7 +28,11 @@ REL_L2 = {torch.float16: 1e-3, torch.bfloat16: 8e-3}
                                                   (16, 100, 12, 64), (1, 1600, 12, 64), (3, 300, 8, 32), (2, 100, 8, 32),
                                                   (2, 300, 12, 32), (5, 37, 4, 16),
                                                   # tcgen05 path (packed qkv, seqlen >= 512, dh >= 32): ragged tails, single-tile last CTA
-                                                  (2, 700, 6, 32), (3, 640, 4, 64), (2, 520, 4, 32), (1, 1153, 4, 64)])
+                                                  (2, 700, 6, 32), (3, 640, 4, 64), (2, 520, 4, 32), (1, 1153, 4, 64),
+                                                  # slot kernel (attn_slots.cu: packed qkv, dh 16 any length, dh 32 windows): lock-step groups of
+                                                  # 1-4 query tiles, ragged key tails, more (window, head) items than slots, single-item launches
+                                                  (3, 300, 4, 16), (2, 129, 4, 16), (1, 1153, 4, 16), (2, 513, 12, 16), (1, 64, 4, 16), (7, 128, 4, 16),
+                                                  (640, 100, 12, 16), (70, 100, 12, 32), (3, 1, 4, 16), (2, 65, 4, 32)])
 def test_attention_matches_softmax_reference(dt, nseq, seqlen, heads, dh):
     from b200 import capi
     g = torch.Generator(device="cuda").manual_seed(seqlen + dh)
@@ -49,7 +53,7 @@ def test_attention_matches_softmax_reference(dt, nseq, seqlen, heads, dh):
 
 
 @pytest.mark.parametrize("dt", DTYPES)
-@pytest.mark.parametrize("dh", [32, 64])
+@pytest.mark.parametrize("dh", [16, 32, 64])
 def test_attention_late_dominant_keys(dt, dh):
     """Keys whose scores dwarf everything seen before arrive late in the sequence: the lazily tracked row maximum of
     the tcgen05 kernel has to move (O rescaled in TMEM) several times, and rows must still normalise exactly."""

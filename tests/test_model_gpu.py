@@ -26,8 +26,8 @@ sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(
 #   bf16 boxes  max    1.5e-3        7.0e-3     3.5e-3  <- same reason with 2^-8 stores: measured 1.5-2.5e-3 (aux layers highest)
 # "block" (ViT residual stream) is looser than 3x autocast for the same reason (16-bit residual stream between blocks).
 TOL = {
-    torch.float16: dict(block=2e-3, memory=2.7e-3, score=1.4e-2, logits_rel=1.5e-3, logits_abs=1.5e-2, boxes=5e-4, dec=3.6e-3),
-    torch.bfloat16: dict(block=1.5e-2, memory=2.2e-2, score=1.0e-1, logits_rel=6e-3, logits_abs=8e-2, boxes=3.5e-3, dec=3e-2),
+    torch.float16: dict(block=2e-3, memory=2.7e-3, score=1.4e-2, logits_rel=1.5e-3, logits_abs=1.5e-2, boxes=8.5e-4, dec=3.6e-3),
+    torch.bfloat16: dict(block=1.5e-2, memory=2.2e-2, score=1.0e-1, logits_rel=6e-3, logits_abs=8e-2, boxes=7e-3, dec=3e-2),
 }
 CASES = [("tiny", 2), ("small", 2), ("medium", 1), ("large", 1), ("xlarge", 1)]
 
@@ -90,11 +90,10 @@ def test_cuda_graph_replay_matches_eager_and_drop_in_module_call():
         model.class_embed.bias.add_(1.0)
     out2 = model(xs[0])
     assert (out2["pred_logits"] - eager[0]["pred_logits"] - 1.0).abs().max().item() < 2e-2
-    # padded batches are rejected, not silently mis-computed
-    from util.misc import nested_tensor_from_tensor_list
-    nt = nested_tensor_from_tensor_list([xs[0][0], xs[0][1][:, :600, :]])
-    with pytest.raises(NotImplementedError):
-        model(nt)
+    # graphs are keyed on the planned batch only: a fresh input tensor (new pointer) replays the same graph
+    fresh = xs[1].clone()
+    out3 = model(fresh)
+    assert torch.equal(out3["pred_logits"], eager[1]["pred_logits"])
 
 
 @pytest.mark.parametrize("name,batch,dt", [("small", 32, torch.float16), ("medium", 16, torch.bfloat16)])
@@ -124,6 +123,101 @@ def test_full_size_batch_is_consistent_with_small_batches(name, batch, dt):
             dl = (small["pred_logits"][rows] - big["pred_logits"][lo:lo + 2][rows]).abs().max().item()
             db = (small["pred_boxes"][rows] - big["pred_boxes"][lo:lo + 2][rows]).abs().max().item()
             assert dl <= tol_l and db <= tol_b, (dl, db)
+
+
+@pytest.mark.parametrize("dt", [torch.float16, torch.bfloat16])
+def test_padded_batch_matches_reference_golden(dt):
+    """a padded / mixed-size batch (NestedTensor.mask not all False) through the C ABI against the
+    REFERENCE's own output (tests/golden/ref_tiny_padded.npz) and the oracle: nearest-resized level masks, valid ratios on
+    the reference boxes, per-image proposals, masked memory rows and masked value rows."""
+    import numpy as np
+    from b200 import capi
+    from b200.config import CONFIGS
+    from b200.synth import synth_images, synth_state_dict
+    from models.lwdetr import LWDETR
+    from oracle import lwdetr_oracle as orc
+    from util.misc import nested_tensor_from_tensor_list
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_tiny_padded.npz"))
+    cfg = CONFIGS["tiny"]
+    B, wseed, iseed = (int(v) for v in g["meta"])
+    x = synth_images(B, iseed).clone()
+    mask = torch.zeros(B, 640, 640, dtype=torch.bool)
+    for b, (h, w) in enumerate(g["valid"]):
+        mask[b, int(h):, :] = True
+        mask[b, :, int(w):] = True
+        x[b][:, mask[b]] = 0
+    sd = synth_state_dict(cfg, wseed)
+    inter = {}
+    ref = orc.forward(sd, cfg, x, mask=mask, inter=inter)
+    eng = capi.Engine(cfg, dt)
+    eng.load_state_dict(sd)
+    forced = eng.forward(x.cuda(), mask=mask.cuda(), topk_override=inter["topk"])
+    tol = TOL[dt]
+    gl, gb = torch.from_numpy(g["pred_logits"]), torch.from_numpy(g["pred_boxes"])
+    assert parity_rel(forced["pred_logits"].cpu(), gl) <= tol["logits_rel"]
+    assert (forced["pred_logits"].cpu() - gl).abs().max().item() <= tol["logits_abs"]
+    assert (forced["pred_boxes"].cpu() - gb).abs().max().item() <= tol["boxes"]
+    assert (forced["enc_outputs"]["pred_boxes"].cpu() - torch.from_numpy(g["enc_boxes"])).abs().max().item() <= tol["boxes"]
+    for a, r in zip(forced["aux_outputs"], ref["aux_outputs"]):
+        assert (a["pred_boxes"].cpu() - r["pred_boxes"]).abs().max().item() <= tol["boxes"]
+    # the mask matters on the device as well, and free-running selection agrees with the oracle's
+    plain = eng.forward(x.cuda(), topk_override=inter["topk"])
+    assert (plain["pred_logits"] - forced["pred_logits"]).abs().max().item() > 1e-2
+    free = eng.forward(x.cuda(), mask=mask.cuda())
+    ti = free["topk_index"].cpu().long()
+    for b in range(B):
+        assert len(set(ti[b].tolist()) & set(inter["topk"][b].tolist())) >= 0.95 * cfg.num_queries
+    # the public module call builds the same mask from a list of differently sized images (util/misc.py:317-339)
+    model = LWDETR(cfg, compute_dtype=dt).eval()
+    model.load_state_dict(sd, strict=True)
+    model.cuda()
+    imgs = [x[b][:, : int(h), : int(w)].cuda() for b, (h, w) in enumerate(g["valid"])]
+    out = model(nested_tensor_from_tensor_list(imgs))
+    assert torch.equal(out["pred_logits"], free["pred_logits"]) and torch.equal(out["pred_boxes"], free["pred_boxes"])
+    eng.close()
+
+
+def parity_rel(a, b):
+    return ((a - b).norm() / (b.norm() + 1e-12)).item()
+
+
+def test_uint8_input_equals_normalised_float_input():
+    """uint8 HWC images with ToTensor's /255 and Normalize(mean, std) fused into the patch gather give the
+    predictions of the same pixels normalised by torch first (demo/demo.py:146-159) - bit for bit, since both paths round the
+    same fp32 values to 16 bits before the patch-embedding GEMM."""
+    from b200 import capi
+    from b200.config import CONFIGS
+    from b200.synth import synth_state_dict
+    cfg = CONFIGS["tiny"]
+    eng = capi.Engine(cfg, torch.float16)
+    eng.load_state_dict(synth_state_dict(cfg, 1))
+    g = torch.Generator().manual_seed(0)
+    u8 = torch.randint(0, 256, (3, 640, 640, 3), generator=g, dtype=torch.uint8)
+    mean, std = torch.tensor(capi.IMAGENET_MEAN), torch.tensor(capi.IMAGENET_STD)
+    f32 = ((u8.float() / 255.0 - mean) / std).permute(0, 3, 1, 2).contiguous()          # ToTensor + Normalize
+    a = {k: v.clone() for k, v in eng.forward(f32.cuda(), want_aux=False).items()}
+    b = eng.forward(u8.cuda(), want_aux=False)
+    assert torch.equal(a["pred_logits"], b["pred_logits"]) and torch.equal(a["pred_boxes"], b["pred_boxes"])
+    eng.close()
+
+
+def test_export_tuple_equals_dict_outputs():
+    """LWDETR.export() (lwdetr.py:103-109): forward becomes forward_export and returns (pred_boxes, pred_logits) of the last
+    decoder layer for a plain [B,3,H,W] tensor - the reference's contract, pinned on the CPU by
+    tests/test_spec_and_oracle.py::test_reference_forward_export_is_the_last_layer_tuple."""
+    from b200.config import CONFIGS
+    from b200.synth import synth_images, synth_state_dict
+    from models.lwdetr import LWDETR
+    cfg = CONFIGS["tiny"]
+    model = LWDETR(cfg, compute_dtype=torch.float16).eval()
+    model.load_state_dict(synth_state_dict(cfg, 1), strict=True)
+    model.cuda()
+    x = synth_images(2, 4).cuda()
+    ref = {k: v.clone() for k, v in model(x).items() if k.startswith("pred")}
+    model.export()
+    out = model(x)
+    assert isinstance(out, tuple) and len(out) == 2
+    assert torch.equal(out[0], ref["pred_boxes"]) and torch.equal(out[1], ref["pred_logits"])
 
 
 # BASELINE.json configs[1..4]: the batch sizes bench.py measures.  GEMM tile choice, persistent-CTA work splits, attention

@@ -119,6 +119,34 @@ def test_oracle_matches_live_reference_with_forced_topk():
     assert (out["pred_boxes"] - ref["pred_boxes"]).abs().max().item() < 1e-5
 
 
+def _have_reference():
+    import ref_import
+    return ref_import.available()
+
+
+@pytest.mark.skipif(not _have_reference(), reason="reference tree not present (neither /root/reference nor baseline/_ref)")
+def test_reference_forward_export_is_the_last_layer_tuple():
+    """SURVEY.md 8f-4, first half: after LWDETR.export() the reference's forward IS forward_export (lwdetr.py:103-109,
+    176-195).  With the decoder in export mode only the last layer's hidden state is returned (transformer.py:406-414),
+    so the tuple is (pred_boxes [B,nq,4], pred_logits [B,nq,C]) of the LAST decoder layer - bit-identical to the dict
+    forward's pred_* on the same input.  This is the contract models.lwdetr.LWDETR.export() of the drop-in implements
+    (checked against the device path in tests/test_model_gpu.py::test_export_tuple_equals_dict_outputs)."""
+    import ref_import
+    cfg = CONFIGS["tiny"]
+    model, _, _ = ref_import.build_reference(cfg)
+    sd = synth_state_dict(cfg, 5)
+    model.load_state_dict(sd, strict=True)
+    x = synth_images(1, 9)
+    with torch.no_grad():
+        ref = model(x)
+        model.export()
+        boxes, logits = model(x)
+    assert boxes.shape == (1, cfg.num_queries, 4) and logits.shape == (1, cfg.num_queries, cfg.num_classes)
+    assert torch.equal(boxes, ref["pred_boxes"]) and torch.equal(logits, ref["pred_logits"])
+    out = orc.forward(sd, cfg, x)
+    assert (out["pred_logits"] - logits).abs().max().item() < 1e-4 and (out["pred_boxes"] - boxes).abs().max().item() < 1e-5
+
+
 @pytest.mark.parametrize("name", ["tiny", "small", "medium", "large", "xlarge"])
 def test_oracle_postprocess_matches_reference_golden(name):
     """oracle.postprocess == the reference's PostProcess.forward (lwdetr.py:515-544) run on the reference's own golden
