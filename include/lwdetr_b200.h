@@ -25,6 +25,9 @@ enum { LWDETR_F16 = 0, LWDETR_BF16 = 1 };
 enum { LWDETR_ACT_NONE = 0, LWDETR_ACT_RELU = 1, LWDETR_ACT_GELU = 2, LWDETR_ACT_SILU = 3 };
 
 LWDETR_API const char* lwdetr_last_error(void);
+/* Debug aid: with LWDETR_B200_DEBUG_WAIT=1 in the environment the attention kernel's barrier waits time out after ~50 ms and
+ * record where; this prints the records to stderr (they live in mapped host memory and survive the device fault). */
+LWDETR_API int lwdetr_debug_dump(void);
 LWDETR_API int lwdetr_abi_version(void);
 
 /* ------------------------------------------------------------------------------------------------

@@ -16,7 +16,8 @@
 //     an integer add; max relative error 7.5e-5, an order of magnitude below the 16-bit rounding of P).  Measured on the
 //     B200 (tools/ubench/softmax_rate.cu, profiles/r02a_ubench_softmax.txt): 0.0486 clk/score/SM against the 0.0625
 //     MUFU floor; more than 3/8 makes the issue slots the bottleneck again.
-//   * setmaxnreg moves registers from the driver warps (56) to the softmax warps (112), which hold a 64-score row chunk.
+//   * setmaxnreg moves registers from the driver warps (96 -> 64) to the softmax warps (96 -> 104), which hold a 64-score row
+//     chunk.  The pool is per CTA: what the 16 softmax warps take (16*32*8) must not exceed what the 4 driver warps release.
 //
 // Two work decompositions share the code (template SHARED):
 //   SHARED = true  (sequences longer than one tile, e.g. 1600 tokens): the four slots of a CTA take up to four consecutive
@@ -31,6 +32,9 @@
 #include "tma_util.h"
 
 #include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
 #include <string>
 #include <type_traits>
 
@@ -83,6 +87,15 @@ __device__ __forceinline__ void st_x16(uint32_t taddr, const uint32_t* r) {
       "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
       : "memory");
 }
+__device__ __forceinline__ void tmem_ld_x8(uint32_t taddr, float (&v)[8]) {
+  uint32_t r[8];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
 __device__ __forceinline__ void st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ float ex2(float x) {
   float y;
@@ -108,31 +121,64 @@ __device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
 template <int N> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
 template <int N> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
 
-// 2^(s*c - m) for a pair without the MUFU: t = round(s*c - m) + MAGIC by one FFMA2, fraction by a second one, degree-3
-// polynomial, exponent added as an integer.  Arguments below -126 are clamped (the result is then ~1e-38 * poly: harmless).
-__device__ __forceinline__ void exp2_poly_pair(uint64_t s2, uint64_t c2, uint64_t magic_minus_m2, uint64_t negm2, float& e0, float& e1) {
+// 2^(s*c - m) for a pair without the MUFU: t = round(s*c - m) + MAGIC by one FFMA2, fraction f = s*c - m - round(..) in
+// [-0.5, 0.5] by a second one, degree-3 polynomial for 2^f, exponent added as an integer.  The raw scores are clamped at
+// smin = m - 125/c first: below that 2^x is 0 for every purpose here, and an unclamped argument would leave f outside the
+// polynomial's range - where it has a root, i.e. an exponent field that wraps into a huge value when the integer is added.
+__device__ __forceinline__ void exp2_poly_pair(float s0, float s1, float smin, uint64_t c2, uint64_t magic_minus_m2, uint64_t negm2, float& e0,
+                                               float& e1) {
+  const uint64_t s2 = pk2(fmaxf(s0, smin), fmaxf(s1, smin));
   const uint64_t t2 = fma2(s2, c2, magic_minus_m2);
-  float t0, t1;
-  upk2(t2, t0, t1);
-  t0 = fmaxf(t0, MAGIC - 126.f);
-  t1 = fmaxf(t1, MAGIC - 126.f);
-  const uint64_t r2 = add2(pk2(t0, t1), pk2(-MAGIC, -MAGIC));
+  const uint64_t r2 = add2(t2, pk2(-MAGIC, -MAGIC));
   const uint64_t u2 = fma2(r2, pk2(-1.f, -1.f), negm2);
   const uint64_t f2 = fma2(s2, c2, u2);
   uint64_t p2 = fma2(f2, pk2(0.05517164617776871f, 0.05517164617776871f), pk2(0.2426111251115799f, 0.2426111251115799f));
   p2 = fma2(p2, f2, pk2(0.6932609677314758f, 0.6932609677314758f));
   p2 = fma2(p2, f2, pk2(0.9999280571937561f, 0.9999280571937561f));
-  float p0, p1;
+  float p0, p1, t0, t1;
   upk2(p2, p0, p1);
+  upk2(t2, t0, t1);
   e0 = __int_as_float(__float_as_int(p0) + (__float_as_int(t0) << 23));
   e1 = __int_as_float(__float_as_int(p1) + (__float_as_int(t1) << 23));
 }
 
+// Debug aid (LWDETR_B200_DEBUG_WAIT=1): barrier waits time out after ~50 ms and leave a record (source line, CTA, warp,
+// parity) in MAPPED HOST memory before trapping - readable after the device fault, see attention_slots_debug_dump().
+struct WaitDbg {
+  unsigned int n;
+  unsigned int rec[64][4];
+};
+__device__ __forceinline__ void wait_tag(uint64_t* bar, uint32_t parity, WaitDbg* dbg, int tag) {
+  if (dbg == nullptr) {
+    mbar_wait(bar, parity);
+    return;
+  }
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 100000000LL) {
+      if ((threadIdx.x & 31) == 0 || true) {
+        const unsigned i = atomicAdd(&dbg->n, 1u);
+        if (i < 64) {
+          dbg->rec[i][0] = static_cast<unsigned>(tag);
+          dbg->rec[i][1] = blockIdx.x;
+          dbg->rec[i][2] = threadIdx.x;
+          dbg->rec[i][3] = parity;
+        }
+        __threadfence_system();
+      }
+      __trap();
+    }
+  }
+}
+#define SL_WAIT(bar, par) wait_tag(bar, par, p.dbg, __LINE__)
+
 struct SlotArgs {
+  WaitDbg* dbg;
   void* o;
   int ldo;
   int seqlen, nseq, heads;
-  float scale_log2;
+  float scale_log2, inv_scale_log2;
   int C;          // column distance between the q, k and v blocks of the packed matrix
   int qtiles;     // 128-row query tiles per sequence
   int ngroups;    // SHARED: CTA items per (sequence, head)
@@ -148,8 +194,9 @@ struct Geo {
   static constexpr int STAGE_BYTES = 2 * KV_BYTES;
   static constexpr int SMEM_Q = SLOTS * 2 * Q_BYTES;
   static constexpr int SMEM_RING = NRINGS * STAGES * STAGE_BYTES;
-  static constexpr int NBAR = 7 * SLOTS + 2 * NRINGS * STAGES;
-  static constexpr int SMEM = 1024 + SMEM_Q + SMEM_RING + NBAR * 8 + 64;
+  static constexpr int NBAR = 10 * SLOTS + 2 * NRINGS * STAGES;
+  static constexpr int SMEM = 1024 + SMEM_Q + SMEM_RING + 1024 + 512 + 64;  // ... | barriers + TMEM slot (1 KB) | ones tile (512 B)
+  static_assert(NBAR * 8 + 16 <= 1024, "barrier block");
   static constexpr uint32_t SLOT_COLS = 128;                   // S 64 | P 32 | O DH (<= 32): four slots fill the 512 columns
 };
 
@@ -161,14 +208,20 @@ __global__ void __launch_bounds__(THREADS, 1) attn_slots_kernel(const __grid_con
   constexpr uint32_t PITCH = DH * 2;
   constexpr uint32_t LAYOUT = DH == 64 ? 2u : (DH == 32 ? 4u : 6u);   // SWIZZLE_128B / 64B / 32B
   constexpr uint32_t SBO = 8 * PITCH;
-  constexpr uint32_t COL_S = 0, COL_P = 64, COL_O = 96;
+  constexpr uint32_t COL_S = 0, COL_P = 64, COL_O = 96, COL_L = 112;
+  // Head dim 16 leaves 16 TMEM columns per slot: the row sums l = sum_k P come from the tensor core too (P times a 16 x 16
+  // tile of ones, four extra N = 16 MMAs per chunk on a pipe that is ~10 % busy) instead of one FADD2 per pair in the
+  // softmax threads, whose instruction stream is what bounds the kernel; l is then the sum of the ROUNDED P, exactly what
+  // the P V product sees.  At head dim 32 the columns are taken by O and the sums stay in registers.
+  constexpr bool SUMS = DH == 16;
   extern __shared__ uint8_t sl_smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(sl_smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = smem;                                          // [slot][2][Q_BYTES]
   uint8_t* sRing = sQ + G::SMEM_Q;                             // [ring][stage][K | V]
   uint64_t* bars = reinterpret_cast<uint64_t*>(sRing + G::SMEM_RING);
-  uint64_t* q_full = bars;                 // [slot]
-  uint64_t* s_full = q_full + SLOTS;       // S(j) written by the tensor core
+  uint64_t* q_full = bars;                 // [slot][2 buffers]
+  uint64_t* q_empty = q_full + 2 * SLOTS;  // [slot][2]: the item's last S MMA has read the Q tile
+  uint64_t* s_full = q_empty + 2 * SLOTS;  // S(j) written by the tensor core
   uint64_t* s_free = s_full + SLOTS;       // the slot's four softmax warps hold S(j) in registers
   uint64_t* p_full = s_free + SLOTS;       // P(j) stored (and O rescaled if the reference maximum moved)
   uint64_t* p_empty = p_full + SLOTS;      // PV(j) completed: P may be overwritten, O is current
@@ -177,13 +230,17 @@ __global__ void __launch_bounds__(THREADS, 1) attn_slots_kernel(const __grid_con
   uint64_t* kv_full = o_free + SLOTS;      // [ring][stage]
   uint64_t* kv_empty = kv_full + G::NRINGS * STAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(kv_empty + G::NRINGS * STAGES);
+  uint8_t* sOnes = sRing + G::SMEM_RING + 1024;                  // 16 x 16 ones (512 B, 256-byte aligned), behind the 1 KB barrier block
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmQ);
     tma_prefetch_desc(&tmKV);
     for (int s = 0; s < SLOTS; ++s) {
-      mbar_init(&q_full[s], 1);
+      for (int b = 0; b < 2; ++b) {
+        mbar_init(&q_full[s * 2 + b], 1);
+        mbar_init(&q_empty[s * 2 + b], 1);
+      }
       mbar_init(&s_full[s], 1);
       mbar_init(&s_free[s], 4);
       mbar_init(&p_full[s], 4);
@@ -200,6 +257,10 @@ __global__ void __launch_bounds__(THREADS, 1) attn_slots_kernel(const __grid_con
   if (warp == 0) {
     tmem_alloc(tmem_slot, 512);
     tmem_relinquish();
+  }
+  if (SUMS && threadIdx.x >= 32 && threadIdx.x < 32 + 128) {
+    reinterpret_cast<uint32_t*>(sOnes)[threadIdx.x - 32] = Cvt<T>::pack(1.f, 1.f);
+    fence_proxy_async_smem();                                    // generic-proxy writes -> visible to the tensor core's reads
   }
   tc_fence_before();
   __syncthreads();
@@ -231,82 +292,130 @@ __global__ void __launch_bounds__(THREADS, 1) attn_slots_kernel(const __grid_con
   const uint32_t tslot = tmem + static_cast<uint32_t>(slot) * G::SLOT_COLS;
 
   if (warp < SLOTS) {
-    reg_dec<56>();
+    reg_dec<64>();
     if (lane == 0) {
       // -------------------------------------------------------------------- driver of one slot: TMA + tcgen05.mma
       constexpr bool BF = Cvt<T>::is_bf16;
       constexpr uint32_t idesc_s = umma_idesc_f16(BF, BM, BK);                 // S: N = 64 keys, Q and K both K-major
       constexpr uint32_t idesc_o = umma_idesc_f16(BF, BM, DH) | (1u << 16);    // O: B (= V) is MN-major
+      constexpr uint32_t idesc_l = umma_idesc_f16(BF, BM, 16);                 // row sums: B = a 16 x 16 tile of ones
       const int ring_id = SHARED ? 0 : slot;
       uint8_t* ring = sRing + ring_id * STAGES * G::STAGE_BYTES;
       uint64_t* rfull = kv_full + ring_id * STAGES;
       uint64_t* rempty = kv_empty + ring_id * STAGES;
       const bool loader = SHARED ? slot == 0 : true;
-      uint32_t n_s = 0, n_pv = 0, n_item = 0, kv_use = 0, kv_load = 0;
-      for (int item = first; item < p.nitems; item += stride) {
-        int seq, head, qtile;
-        const bool active = decode(item, seq, head, qtile);
-        const int row0 = seq * p.seqlen;
-        const int colq = head * DH, colk = p.C + head * DH, colv = 2 * p.C + head * DH;
-        uint8_t* qbuf = sQ + (slot * 2 + (n_item & 1)) * G::Q_BYTES;
-        if (active) {
-          mbar_arrive_expect_tx(&q_full[slot], G::Q_BYTES);
-          tma_load_2d(qbuf, &tmQ, &q_full[slot], colq, row0 + qtile * BM);
-        }
-        auto load_chunk = [&](int c) {
-          const int st = kv_load % STAGES;
-          mbar_wait(&rempty[st], ((kv_load / STAGES) & 1) ^ 1);
+      // The slot's work is a FLAT stream of (item, chunk) steps.  Three cursors walk it in a fixed order - loads run up to
+      // STAGES chunks ahead (non-blocking probe of the ring), S is issued one chunk ahead of the softmax warps, PV follows
+      // the softmax warps - so that the next item's Q, its K/V chunks and its first S are already under way while the
+      // softmax warps finish the tail and the epilogue of the current item.  Every wait in the order below is for something
+      // the other side produces without needing this thread, hence the blocking (suspending) waits.
+      const int n_my = first < p.nitems ? (p.nitems - first + stride - 1) / stride : 0;
+      const uint32_t total = static_cast<uint32_t>(n_my) * nchunks;
+      struct Cur {                     // (item index, chunk) position of a cursor; a / b: what that cursor needs of the item
+        int i, j, a, b;
+        bool active;
+      };
+      auto cur_set = [&](Cur& cu, int i, int kind) {               // kind 0: activity only, 1: loader (row0, head), 2: Q (row, head)
+        int seq = 0, head = 0, qtile = 0;
+        cu.i = i;
+        cu.j = 0;
+        cu.active = i < n_my ? decode(first + i * stride, seq, head, qtile) : false;
+        cu.a = kind == 1 ? seq * p.seqlen : seq * p.seqlen + qtile * BM;
+        cu.b = head * DH;
+      };
+      auto cur_next = [&](Cur& cu, int kind) {
+        if (++cu.j == nchunks) cur_set(cu, cu.i + 1, kind);
+      };
+      Cur L, Sx, Px, Qx;
+      cur_set(L, 0, 1);
+      cur_set(Sx, 0, 0);
+      cur_set(Px, 0, 0);
+      cur_set(Qx, 0, 2);
+      uint32_t lc = 0, sc = 0, pc = 0;
+      uint32_t aq = 0;                 // active items whose Q was requested
+      uint32_t n_s = 0, n_pv = 0;      // S / PV issued by this slot (active items only)
+      uint32_t as_item = 0;            // active items whose S phase is complete
+      uint32_t n_item = 0;             // active items completed (o_full committed)
+      auto load_next_q = [&]() {       // Q tile of the next active item into buffer aq & 1
+        while (Qx.i < n_my && !Qx.active) cur_set(Qx, Qx.i + 1, 2);
+        if (Qx.i >= n_my) return;
+        const uint32_t buf = aq & 1;
+        if (aq >= 2) SL_WAIT(&q_empty[slot * 2 + buf], ((aq >> 1) - 1) & 1);
+        mbar_arrive_expect_tx(&q_full[slot * 2 + buf], G::Q_BYTES);
+        tma_load_2d(sQ + (slot * 2 + buf) * G::Q_BYTES, &tmQ, &q_full[slot * 2 + buf], Qx.b, Qx.a);
+        ++aq;
+        cur_set(Qx, Qx.i + 1, 2);
+      };
+      auto top_up = [&]() {            // K/V chunks as far ahead as the ring allows (in lock-step mode slot 0 loads for everybody)
+        while (loader && lc < total) {
+          const int st = lc % STAGES;
+          if (lc >= static_cast<uint32_t>(STAGES) && !mbar_test(&rempty[st], ((lc / STAGES) - 1) & 1)) break;
+          const int row = L.a + L.j * BK;
           mbar_arrive_expect_tx(&rfull[st], G::STAGE_BYTES);
-          tma_load_2d(ring + st * G::STAGE_BYTES, &tmKV, &rfull[st], colk, row0 + c * BK);
-          tma_load_2d(ring + st * G::STAGE_BYTES + G::KV_BYTES, &tmKV, &rfull[st], colv, row0 + c * BK);
-          ++kv_load;
-        };
-        int next_load = 0;
-        if (loader)
-          for (; next_load < nchunks && next_load < STAGES - 1; ++next_load) load_chunk(next_load);
-        const uint64_t qdesc = desc(smem_u32(qbuf), SBO, LAYOUT);
-        auto issue_s = [&](uint32_t chunk_pos) {                     // S(next) from the K chunk at ring position chunk_pos
-          const int st = chunk_pos % STAGES;
-          mbar_wait(&rfull[st], (chunk_pos / STAGES) & 1);
-          if (!active) return;
-          if (n_s > 0) mbar_wait(&s_free[slot], (n_s - 1) & 1);      // the softmax warps pulled the previous S out of TMEM
+          tma_load_2d(ring + st * G::STAGE_BYTES, &tmKV, &rfull[st], p.C + L.b, row);
+          tma_load_2d(ring + st * G::STAGE_BYTES + G::KV_BYTES, &tmKV, &rfull[st], 2 * p.C + L.b, row);
+          ++lc;
+          cur_next(L, 1);
+        }
+      };
+      auto issue_s = [&]() {           // S(sc) = Q K^T
+        const int st = sc % STAGES;
+        SL_WAIT(&rfull[st], (sc / STAGES) & 1);
+        if (Sx.active) {
+          const uint32_t buf = as_item & 1;
+          if (Sx.j == 0) SL_WAIT(&q_full[slot * 2 + buf], (as_item >> 1) & 1);
+          if (n_s > 0) SL_WAIT(&s_free[slot], (n_s - 1) & 1);        // the softmax warps pulled the previous S out of TMEM
           tc_fence_after();
+          const uint64_t qdesc = desc(smem_u32(sQ + (slot * 2 + buf) * G::Q_BYTES), SBO, LAYOUT);
           const uint64_t kdesc = desc(smem_u32(ring + st * G::STAGE_BYTES), SBO, LAYOUT);
 #pragma unroll
           for (int kk = 0; kk < DH / 16; ++kk) umma_f16_ss(tslot + COL_S, qdesc + 2 * kk, kdesc + 2 * kk, idesc_s, kk != 0 ? 1u : 0u);
           umma_commit(&s_full[slot]);
           ++n_s;
-        };
-        if (active) mbar_wait(&q_full[slot], n_item & 1);
-        issue_s(kv_use);
-        for (int j = 0; j < nchunks; ++j) {
-          if (j + 1 < nchunks) issue_s(kv_use + 1);                  // S(j+1) runs while the softmax warps work on S(j)
-          const int st = kv_use % STAGES;
-          if (active) {
-            mbar_wait(&p_full[slot], n_pv & 1);                      // P(j) is in TMEM, O carries the current reference maximum
-            if (j == 0 && n_item > 0) mbar_wait(&o_free[slot], (n_item - 1) & 1);   // the previous item's O has been read out
-            tc_fence_after();
-            const uint64_t vdesc = desc(smem_u32(ring + st * G::STAGE_BYTES + G::KV_BYTES), SBO, LAYOUT);
-#pragma unroll
-            for (int kk = 0; kk < BK / 16; ++kk)                     // 16 keys per MMA: A advances 8 TMEM columns, B 16 rows
-              mma_ts(tslot + COL_O, tslot + COL_P + 8 * kk, vdesc + ((16 * PITCH) >> 4) * kk, idesc_o, (j | kk) != 0 ? 1u : 0u);
-            umma_commit(&p_empty[slot]);
-            umma_commit(&rempty[st]);
-            ++n_pv;
-          } else {
-            mbar_arrive(&rempty[st]);                                // an idle slot of a lock-step item still releases the stage
+          if (Sx.j + 1 == nchunks) {                                 // last S of the item: its Q buffer may be refilled once these MMAs are done
+            umma_commit(&q_empty[slot * 2 + buf]);
+            ++as_item;
           }
-          ++kv_use;
-          if (loader && next_load < nchunks) load_chunk(next_load++);
         }
-        if (active) {
-          umma_commit(&o_full[slot]);
-          ++n_item;
+        ++sc;
+        cur_next(Sx, 0);
+      };
+      load_next_q();
+      load_next_q();
+      top_up();
+      if (total > 0) issue_s();
+      while (pc < total) {
+        top_up();
+        if (sc < total) issue_s();                                   // S(pc + 1) runs while the softmax warps work on S(pc)
+        const int st = pc % STAGES;
+        if (Px.active) {
+          SL_WAIT(&p_full[slot], n_pv & 1);                          // P(pc) is in TMEM, O carries the current reference maximum
+          if (Px.j == 0 && n_item > 0) SL_WAIT(&o_free[slot], (n_item - 1) & 1);   // the previous item's O has been read out
+          tc_fence_after();
+          const uint64_t vdesc = desc(smem_u32(ring + st * G::STAGE_BYTES + G::KV_BYTES), SBO, LAYOUT);
+          const uint64_t odesc = desc(smem_u32(sOnes), 256, 6u);
+#pragma unroll
+          for (int kk = 0; kk < BK / 16; ++kk) {                     // 16 keys per MMA: A advances 8 TMEM columns, B 16 rows
+            mma_ts(tslot + COL_O, tslot + COL_P + 8 * kk, vdesc + ((16 * PITCH) >> 4) * kk, idesc_o, (Px.j | kk) != 0 ? 1u : 0u);
+            if (SUMS) mma_ts(tslot + COL_L, tslot + COL_P + 8 * kk, odesc, idesc_l, (Px.j | kk) != 0 ? 1u : 0u);   // row sums of the rounded P
+          }
+          umma_commit(&p_empty[slot]);
+          umma_commit(&rempty[st]);
+          ++n_pv;
+          if (Px.j + 1 == nchunks) {
+            umma_commit(&o_full[slot]);
+            ++n_item;
+            load_next_q();                                           // the Q buffer of the item before this one is free by now
+          }
+        } else {
+          mbar_arrive(&rempty[st]);                                  // an idle slot of a lock-step item still releases the stage
         }
+        ++pc;
+        cur_next(Px, 0);
       }
     }
   } else {
-    reg_inc<112>();
+    reg_inc<104>();
     // ---------------------------------------------------------------------- softmax / epilogue: one thread per query row
     const int quarter = warp & 3;                                  // TMEM lane quarter this warp may access
     const int r = quarter * 32 + lane;
@@ -321,7 +430,7 @@ __global__ void __launch_bounds__(THREADS, 1) attn_slots_kernel(const __grid_con
       uint64_t lsum2 = pk2(0.f, 0.f);
       for (int j = 0; j < nchunks; ++j, ++n_c) {
         float v[64];
-        mbar_wait(&s_full[slot], n_c & 1);
+        SL_WAIT(&s_full[slot], n_c & 1);
         tc_fence_after();
         __syncwarp();
         ld_x32(tbase + COL_S, v);
@@ -331,6 +440,8 @@ __global__ void __launch_bounds__(THREADS, 1) attn_slots_kernel(const __grid_con
         __syncwarp();
         if (lane == 0) mbar_arrive(&s_free[slot]);                 // one elected arrival per warp
         const int nvalid = min(BK, p.seqlen - j * BK);             // keys >= nvalid belong to the next sequence / are padding
+        // ---- row maximum of the valid keys.  Ragged chunks are handled in groups of 8 keys with warp-uniform branches:
+        // full groups take the unmasked code, only the group that holds the boundary pays for per-key predicates.
         float mchunk;
         if (nvalid == BK) {
           float mm[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
@@ -342,60 +453,74 @@ __global__ void __launch_bounds__(THREADS, 1) attn_slots_kernel(const __grid_con
         } else {
           mchunk = -INFINITY;
 #pragma unroll
-          for (int i = 0; i < 64; ++i)
-            if (i < nvalid) mchunk = fmaxf(mchunk, v[i]);
+          for (int g = 0; g < 8; ++g) {
+            if (g * 8 + 8 <= nvalid) {
+              mchunk = fmaxf(mchunk, fmaxf(fmaxf(fmaxf(v[g * 8], v[g * 8 + 1]), fmaxf(v[g * 8 + 2], v[g * 8 + 3])),
+                                           fmaxf(fmaxf(v[g * 8 + 4], v[g * 8 + 5]), fmaxf(v[g * 8 + 6], v[g * 8 + 7]))));
+            } else if (g * 8 < nvalid) {
+#pragma unroll
+              for (int e = 0; e < 8; ++e)
+                if (g * 8 + e < nvalid) mchunk = fmaxf(mchunk, v[g * 8 + e]);
+            }
+          }
         }
         // lazy reference maximum: a row's decision only involves its own thread
         const bool move = (mchunk - m_ref) * c > LAZY_LOG2;        // true at j = 0 (m_ref = -inf)
         const float alpha = move ? ex2((m_ref - mchunk) * c) : 1.f;
         if (move) m_ref = mchunk;
         const float msc = m_ref * c;
-        if (move) lsum2 = fma2(lsum2, pk2(alpha, alpha), pk2(0.f, 0.f));
+        if (!SUMS && move) lsum2 = fma2(lsum2, pk2(alpha, alpha), pk2(0.f, 0.f));
         const uint64_t nm2 = pk2(-msc, -msc), mg2 = pk2(MAGIC - msc, MAGIC - msc);
+        const float smin = m_ref - 125.f * p.inv_scale_log2;       // raw-score floor of the polynomial path
         uint32_t pk[32];
-        auto body = [&](auto tail_tag) {
-          constexpr bool TAIL = decltype(tail_tag)::value;
+        auto group = [&](int g, auto masked_tag) {                 // keys 8g .. 8g+7 -> pk[4g .. 4g+3]
+          constexpr bool MASKED = decltype(masked_tag)::value;
 #pragma unroll
-          for (int g = 0; g < 8; ++g) {
-            if (TAIL && g * 8 >= nvalid) {                          // uniform: nothing valid in this group of 8 keys
-#pragma unroll
-              for (int q = 0; q < 4; ++q) pk[g * 4 + q] = 0u;
-              continue;
+          for (int q = 0; q < 4; ++q) {
+            const int i = g * 4 + q;                               // pair index: keys 2i, 2i+1
+            float e0, e1;
+            if ((PMASK >> (i & 7)) & 1u) {
+              exp2_poly_pair(v[2 * i], v[2 * i + 1], smin, c2, mg2, nm2, e0, e1);
+            } else {
+              float a0, a1;
+              upk2(fma2(pk2(v[2 * i], v[2 * i + 1]), c2, nm2), a0, a1);
+              e0 = ex2(a0);
+              e1 = ex2(a1);
             }
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const int i = g * 4 + q;                              // pair index: keys 2i, 2i+1
-              const uint64_t s2 = pk2(v[2 * i], v[2 * i + 1]);
-              float e0, e1;
-              if ((PMASK >> (i & 7)) & 1u) {
-                exp2_poly_pair(s2, c2, mg2, nm2, e0, e1);
-              } else {
-                float a0, a1;
-                upk2(fma2(s2, c2, nm2), a0, a1);
-                e0 = ex2(a0);
-                e1 = ex2(a1);
-              }
-              if (TAIL) {
-                e0 = 2 * i < nvalid ? e0 : 0.f;
-                e1 = 2 * i + 1 < nvalid ? e1 : 0.f;
-              }
-              pk[i] = Cvt<T>::pack(e0, e1);
-              lsum2 = add2(lsum2, pk2(e0, e1));
+            if (MASKED) {
+              e0 = 2 * i < nvalid ? e0 : 0.f;
+              e1 = 2 * i + 1 < nvalid ? e1 : 0.f;
             }
+            pk[i] = Cvt<T>::pack(e0, e1);
+            if (!SUMS) lsum2 = add2(lsum2, pk2(e0, e1));
           }
         };
-        if (nvalid == BK) body(std::false_type{});
-        else body(std::true_type{});
-        // only now wait for PV(j-1): its latency hides behind the exponentials above (P is single-buffered)
-        if (n_c > 0) mbar_wait(&p_empty[slot], (n_c - 1) & 1);
-        tc_fence_after();
-        if (j > 0 && __any_sync(0xffffffffu, move)) {               // rare after the first chunks: rescale this row of O
+        if (nvalid == BK) {
 #pragma unroll
-          for (int cc = 0; cc < DH / 16; ++cc) {
+          for (int g = 0; g < 8; ++g) group(g, std::false_type{});
+        } else {
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            if (g * 8 + 8 <= nvalid) {
+              group(g, std::false_type{});
+            } else if (g * 8 < nvalid) {
+              group(g, std::true_type{});
+            } else {
+#pragma unroll
+              for (int q = 0; q < 4; ++q) pk[g * 4 + q] = 0u;
+            }
+          }
+        }
+        // only now wait for PV(j-1): its latency hides behind the exponentials above (P is single-buffered)
+        if (n_c > 0) SL_WAIT(&p_empty[slot], (n_c - 1) & 1);
+        tc_fence_after();
+        if (j > 0 && __any_sync(0xffffffffu, move)) {               // rare after the first chunks: rescale this row of O (and of l)
+#pragma unroll
+          for (int cc = 0; cc < (DH + (SUMS ? 16 : 0)) / 16; ++cc) {
             float o16[16];
             uint32_t u16[16];
             __syncwarp();
-            tmem_ld_x16(tbase + COL_O + cc * 16, o16);
+            tmem_ld_x16(tbase + COL_O + cc * 16, o16);              // COL_L directly follows O at head dim 16
             tmem_ld_wait();
 #pragma unroll
             for (int i = 0; i < 16; ++i) u16[i] = __float_as_uint(o16[i] * alpha);
@@ -411,11 +536,20 @@ __global__ void __launch_bounds__(THREADS, 1) attn_slots_kernel(const __grid_con
         if (lane == 0) mbar_arrive(&p_full[slot]);
       }
       // ---- O / l -> global
-      float l0, l1;
-      upk2(lsum2, l0, l1);
-      const float inv = 1.f / (l0 + l1);
-      mbar_wait(&o_full[slot], n_item & 1);
+      SL_WAIT(&o_full[slot], n_item & 1);
       tc_fence_after();
+      float inv;
+      if (SUMS) {
+        float l8[8];
+        __syncwarp();
+        tmem_ld_x8(tbase + COL_L, l8);                              // 16 identical columns: the row sum of the rounded P
+        tmem_ld_wait();
+        inv = 1.f / l8[0];
+      } else {
+        float l0, l1;
+        upk2(lsum2, l0, l1);
+        inv = 1.f / (l0 + l1);
+      }
       const int qrow = qtile * BM + r;
       T* dst = reinterpret_cast<T*>(p.o) + (static_cast<long long>(seq) * p.seqlen + qrow) * p.ldo + head * DH;
       U8 ov[DH / 16];
@@ -446,6 +580,22 @@ __global__ void __launch_bounds__(THREADS, 1) attn_slots_kernel(const __grid_con
   }
 }
 
+static WaitDbg* g_dbg_host = nullptr;
+static WaitDbg* debug_buffer() {
+  static WaitDbg* dev = [] () -> WaitDbg* {
+    const char* e = getenv("LWDETR_B200_DEBUG_WAIT");
+    if (!e || atoi(e) == 0) return nullptr;
+    void* h = nullptr;
+    void* d = nullptr;
+    if (cudaHostAlloc(&h, sizeof(WaitDbg), cudaHostAllocMapped) != cudaSuccess) return nullptr;
+    memset(h, 0, sizeof(WaitDbg));
+    if (cudaHostGetDevicePointer(&d, h, 0) != cudaSuccess) return nullptr;
+    g_dbg_host = static_cast<WaitDbg*>(h);
+    return static_cast<WaitDbg*>(d);
+  }();
+  return dev;
+}
+
 template <typename T, int DH, bool SHARED, uint32_t PMASK>
 static int launch_m(const AttnArgs& a, int C, cudaStream_t st) {
   using G = Geo<DH, SHARED>;
@@ -458,7 +608,8 @@ static int launch_m(const AttnArgs& a, int C, cudaStream_t st) {
   if (tma_encode(&tq, dt, 2, a.q, dims, strides, boxq, DH * 2, &err)) return -3;
   if (tma_encode(&tkv, dt, 2, a.q, dims, strides, boxkv, DH * 2, &err)) return -3;
   SlotArgs p;
-  p.o = a.o; p.ldo = a.ldo; p.seqlen = a.seqlen; p.nseq = a.nseq; p.heads = a.heads; p.scale_log2 = a.scale_log2; p.C = C;
+  p.dbg = debug_buffer();
+  p.o = a.o; p.ldo = a.ldo; p.seqlen = a.seqlen; p.nseq = a.nseq; p.heads = a.heads; p.scale_log2 = a.scale_log2; p.inv_scale_log2 = 1.f / a.scale_log2; p.C = C;
   p.qtiles = (a.seqlen + BM - 1) / BM;
   p.ngroups = (p.qtiles + SLOTS - 1) / SLOTS;
   const long long sh = static_cast<long long>(a.nseq) * a.heads;
@@ -487,6 +638,16 @@ static int launch(const AttnArgs& a, int C, cudaStream_t st) {
 }
 
 }  // namespace sl
+
+// prints (stderr) the barrier waits that timed out under LWDETR_B200_DEBUG_WAIT=1; returns their number
+int attention_slots_debug_dump() {
+  if (!sl::g_dbg_host) return 0;
+  const unsigned n = sl::g_dbg_host->n;
+  for (unsigned i = 0; i < n && i < 64; ++i)
+    fprintf(stderr, "attn_slots wait timeout: line %u  cta %u  thread %u (warp %u)  parity %u\n", sl::g_dbg_host->rec[i][0], sl::g_dbg_host->rec[i][1],
+            sl::g_dbg_host->rec[i][2], sl::g_dbg_host->rec[i][2] >> 5, sl::g_dbg_host->rec[i][3]);
+  return static_cast<int>(n);
+}
 
 // Packed-qkv path for head dims 16 / 32: q, k, v are the column blocks [0,C), [C,2C), [2C,3C) of one 16-bit matrix.
 int attention_slots_launch(int dtype, const AttnArgs& a, int dh, int C, cudaStream_t st) {

@@ -46,6 +46,31 @@ __device__ __forceinline__ float gelu_erf(float x) {
   return fmaf(-ax * t, p * e, fmaxf(x, 0.f));
 }
 
+// The same exact-erf GELU for a PAIR on the packed fp32x2 pipe, without the MUFU: gelu(x) = x * (0.5 + xc * q(xc^2)), xc = x
+// clamped to [-4.5, 4.5], q a degree-9 polynomial fitted to erf(x/sqrt2) / (2x) (weighted least squares at Chebyshev nodes;
+// fp32 Horner: max |error| 7.4e-5 at |x| ~ 4.46 where gelu ~ 4.46, < 1e-6 for |x| < 3; beyond the clamp Phi(-4.5) = 3.4e-6
+// multiplies x).  16 instructions per pair (8 per element) against 14 per element for gelu_erf - the fc1 epilogue is bound by
+// its instruction count, not by the tensor core.
+__device__ __forceinline__ uint64_t gelu_erf2(uint64_t x2) {
+  float x0, x1;
+  f2_unpack(x2, x0, x1);
+  const uint64_t xc = f2_pack(fminf(fmaxf(x0, -4.5f), 4.5f), fminf(fmaxf(x1, -4.5f), 4.5f));
+  const uint64_t u = f2_mul(xc, xc);
+#define LWB_K2(v) f2_pack(v, v)
+  uint64_t q = f2_fma(LWB_K2(-1.3369040159e-12f), u, LWB_K2(1.6336444415e-10f));
+  q = f2_fma(q, u, LWB_K2(-8.9213697499e-09f));
+  q = f2_fma(q, u, LWB_K2(2.8944761772e-07f));
+  q = f2_fma(q, u, LWB_K2(-6.2733902842e-06f));
+  q = f2_fma(q, u, LWB_K2(9.7063541348e-05f));
+  q = f2_fma(q, u, LWB_K2(-1.1183810776e-03f));
+  q = f2_fma(q, u, LWB_K2(9.8202145566e-03f));
+  q = f2_fma(q, u, LWB_K2(-6.6317755718e-02f));
+  q = f2_fma(q, u, LWB_K2(3.9887377948e-01f));
+  const uint64_t t = f2_fma(xc, q, LWB_K2(0.5f));
+#undef LWB_K2
+  return f2_mul(x2, t);
+}
+
 struct TileCoord {
   int m_tile, n_tile, n0, cb, cy0, cx0;
 };
@@ -281,51 +306,69 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int nrem = p.N - n;                     // may be <= 0 for the padded tail of the last n-tile
         if (!valid || nrem <= 0) return;
         const bool full = nrem >= 16;
-        if (ln_in) {
-          const float4* sc = reinterpret_cast<const float4*>(s_csum + c * 16);
+        // packed fp32x2 from here on (FFMA2 / FADD2 / FMUL2): half the issue slots of the scalar form
+        uint64_t w[8];
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float4 c4 = lds128(reinterpret_cast<const float*>(sc + j));
-            v[4 * j] = ln_rstd * fmaf(-ln_mean, c4.x, v[4 * j]);
-            v[4 * j + 1] = ln_rstd * fmaf(-ln_mean, c4.y, v[4 * j + 1]);
-            v[4 * j + 2] = ln_rstd * fmaf(-ln_mean, c4.z, v[4 * j + 2]);
-            v[4 * j + 3] = ln_rstd * fmaf(-ln_mean, c4.w, v[4 * j + 3]);
-          }
-        }
+        for (int j = 0; j < 8; ++j) w[j] = f2_pack(v[2 * j], v[2 * j + 1]);
         {
           const float4* sb = reinterpret_cast<const float4*>(s_bias + c * 16);
+          if (ln_in) {
+            // rstd*(acc - mean*colsum) + bias  ==  a*acc + (b*colsum + bias),  a = rstd, b = -rstd*mean
+            const uint64_t a2 = f2_pack(ln_rstd, ln_rstd), b2 = f2_pack(-ln_rstd * ln_mean, -ln_rstd * ln_mean);
+            const float4* sc = reinterpret_cast<const float4*>(s_csum + c * 16);
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float4 b4 = lds128(reinterpret_cast<const float*>(sb + j));
-            v[4 * j] += b4.x; v[4 * j + 1] += b4.y; v[4 * j + 2] += b4.z; v[4 * j + 3] += b4.w;
+            for (int j = 0; j < 4; ++j) {
+              const float4 c4 = lds128(reinterpret_cast<const float*>(sc + j));
+              const float4 b4 = lds128(reinterpret_cast<const float*>(sb + j));
+              w[2 * j] = f2_fma(a2, w[2 * j], f2_fma(b2, f2_pack(c4.x, c4.y), f2_pack(b4.x, b4.y)));
+              w[2 * j + 1] = f2_fma(a2, w[2 * j + 1], f2_fma(b2, f2_pack(c4.z, c4.w), f2_pack(b4.z, b4.w)));
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float4 b4 = lds128(reinterpret_cast<const float*>(sb + j));
+              w[2 * j] = f2_add(w[2 * j], f2_pack(b4.x, b4.y));
+              w[2 * j + 1] = f2_add(w[2 * j + 1], f2_pack(b4.z, b4.w));
+            }
           }
         }
         if (act == ACT_GELU) {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] = gelu_erf(v[j]);
+          for (int j = 0; j < 8; ++j) w[j] = gelu_erf2(w[j]);
         } else if (act == ACT_RELU) {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
+          for (int j = 0; j < 8; ++j) {
+            float a, b;
+            f2_unpack(w[j], a, b);
+            w[j] = f2_pack(fmaxf(a, 0.f), fmaxf(b, 0.f));
+          }
         } else if (act == ACT_SILU) {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] = __fdividef(v[j], 1.f + __expf(-v[j]));
+          for (int j = 0; j < 8; ++j) {
+            float a, b;
+            f2_unpack(w[j], a, b);
+            w[j] = f2_pack(__fdividef(a, 1.f + __expf(-a)), __fdividef(b, 1.f + __expf(-b)));
+          }
         }
         if (has_gamma) {
           const float4* sg = reinterpret_cast<const float4*>(s_gamma + c * 16);
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             const float4 g4 = lds128(reinterpret_cast<const float*>(sg + j));
-            v[4 * j] *= g4.x; v[4 * j + 1] *= g4.y; v[4 * j + 2] *= g4.z; v[4 * j + 3] *= g4.w;
+            w[2 * j] = f2_mul(w[2 * j], f2_pack(g4.x, g4.y));
+            w[2 * j + 1] = f2_mul(w[2 * j + 1], f2_pack(g4.z, g4.w));
           }
         }
         if (rvec) {
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const float2 f = Cvt<T>::unpack(rr.v[j]);
-            v[2 * j] += f.x;
-            v[2 * j + 1] += f.y;
+            w[j] = f2_add(w[j], f2_pack(f.x, f.y));
           }
-        } else if ((GEN || EP == EP_RESID) && resid_row != nullptr) {
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f2_unpack(w[j], v[2 * j], v[2 * j + 1]);
+        if (!rvec && (GEN || EP == EP_RESID) && resid_row != nullptr) {
           for (int j = 0; j < 16; ++j)
             if (j < nrem) v[j] += Cvt<T>::to_f(resid_row[n + j]);
         }

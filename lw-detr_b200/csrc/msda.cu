@@ -7,10 +7,11 @@
 // 1. msda_fwd_kernel - the model path.  The reference gathers 32-byte head slices from a token-major value tensor:
 //    every bilinear corner is a random DRAM sector.  Here value_proj writes the value tensor HEAD-MAJOR
 //    ([image][head][token][16], gemm_tc "head-major" epilogue), so everything one (image, head) can ever sample is
-//    ONE contiguous slab (51 KB at 40x40).  Persistent CTAs (one per SM) walk the (image, head) items: a producer
-//    warp streams the slab - in bands of <= 1680 tokens - into a 4-stage shared-memory ring with 1-D bulk copies
-//    (cp.async.bulk + mbarrier complete_tx), 19 consumer warps (thread = 8 channels of one query) take the bilinear
-//    corners out of shared memory.  DRAM sees the value tensor exactly once, as a linear stream; the softmax over
+//    ONE contiguous slab (51 KB at 40x40).  Persistent CTAs (one per SM, two independent halves of 10 warps) walk the
+//    (image, head) items: the slab is streamed - in bands of <= 1680 tokens - into a two-stage shared-memory ring per
+//    half with 1-D bulk copies (cp.async.bulk + mbarrier complete_tx; measured 7.0 TB/s at this chunk size,
+//    profiles/r02c_ubench_stream.txt), the threads (one = all 16 channels of one query) take the bilinear corners out
+//    of shared memory.  DRAM sees the value tensor exactly once, as a linear stream; the softmax over
 //    the L*P logits, the sampling-location arithmetic (incl. valid ratios of padded batches) and the weighted sum
 //    stay in registers; the raw projections of the NEXT item are prefetched while the current one is sampled.
 //    A P3 level (80x80 = 205 KB per head) does not fit a stage: it is cut into bands of 21 rows (one halo row), each
@@ -27,31 +28,40 @@
 
 namespace lwb {
 
-static constexpr int MS_STAGES = 4;
+static constexpr int MS_STAGES = 4;                                // two per consumer group
 static constexpr int MS_STAGE_TOKENS = 1680;                       // 21 rows of 80 / 42 rows of 40
 static constexpr int MS_STAGE_BYTES = MS_STAGE_TOKENS * MSDA_D * 2;
-static constexpr int MS_CONSUMER_WARPS = 19;                       // 608 threads = 304 queries x 2 channel halves; 20 warps in all => 96 registers/thread
-static constexpr int MS_QPASS = MS_CONSUMER_WARPS * 16;            // queries per pass
-static constexpr int MS_THREADS = 32 * (1 + MS_CONSUMER_WARPS);
+static constexpr int MS_GROUP_WARPS = 10;                          // 320 threads = 320 queries per pass
+static constexpr int MS_QPASS = MS_GROUP_WARPS * 32;
+static constexpr int MS_THREADS = 2 * MS_QPASS;                    // 20 warps => 96 registers / thread
 static constexpr int MS_SMEM = MS_STAGES * MS_STAGE_BYTES + 128;
 
-__device__ __forceinline__ U4 lds16(const void* p) {
+__device__ __forceinline__ U4 lds16(uint32_t addr) {
   U4 r;
-  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(smem_u32(p)));
+  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr));
   return r;
 }
 
+// ncu of the first version of this kernel (profiles/r02d_ncu_msda_small.txt) showed it bound by its own instruction
+// stream, not by memory: 550 instructions per (query, head, 8-channel half) - half of them index / predicate arithmetic
+// that both halves repeated, plus one conversion and one FFMA per value.  Hence: ONE thread owns all 16 channels of a
+// (query, head) (the scalar work is done once), the accumulation runs on packed fp32x2 FMAs, addresses are 32-bit
+// shared-memory offsets.  The CTA is two independent halves of 10 warps, each walking its own (image, head) items with
+// its own two-stage ring; lane 0 of each half's first warp is its producer (it re-arms a stage as soon as its half has
+// released it), so a slab is loading for each half while the other slab is being sampled.
 template <typename T, int NL, int NP>   // levels, points per head and level
 __global__ void __launch_bounds__(MS_THREADS, 1) msda_fwd_kernel(const __grid_constant__ MsdaArgs p) {
   constexpr int LP = NL * NP;
   extern __shared__ __align__(128) uint8_t ms_smem[];
   uint64_t* full = reinterpret_cast<uint64_t*>(ms_smem + MS_STAGES * MS_STAGE_BYTES);
   uint64_t* empty = full + MS_STAGES;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int grp = threadIdx.x / MS_QPASS;                     // consumer half 0 / 1
+  const int gt = threadIdx.x - grp * MS_QPASS;                // thread in the half = query index in a pass
+  const int lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
     for (int s = 0; s < MS_STAGES; ++s) {
       mbar_init(&full[s], 1);
-      mbar_init(&empty[s], MS_CONSUMER_WARPS);
+      mbar_init(&empty[s], MS_GROUP_WARPS);
     }
     fence_mbar_init();
   }
@@ -59,38 +69,36 @@ __global__ void __launch_bounds__(MS_THREADS, 1) msda_fwd_kernel(const __grid_co
   pdl_sync();   // programmatic dependent launch: release the successor, wait for the predecessor (launch.h)
   const int nitems = p.batch * p.heads;
   const int npass = (p.nq + MS_QPASS - 1) / MS_QPASS;
-
-  if (warp == 0) {
-    if (lane == 0) {
-      // ------------------------------------------------------------------ producer: slabs -> shared-memory ring
-      uint32_t ring = 0;
-      for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
-        const int b = item / p.heads, m = item - b * p.heads;
-        const T* slab = reinterpret_cast<const T*>(p.value) + static_cast<long long>(b) * p.v_b_stride + static_cast<long long>(m) * p.S * MSDA_D;
-        for (int pass = 0; pass < npass; ++pass)
-          for (int k = 0; k < p.nbands; ++k, ++ring) {
-            const int s = ring % MS_STAGES;
-            mbar_wait(&empty[s], ((ring / MS_STAGES) & 1) ^ 1);
-            mbar_arrive_expect_tx(&full[s], static_cast<uint32_t>(p.bands[k].bytes));
-            bulk_load(ms_smem + s * MS_STAGE_BYTES, slab + static_cast<long long>(p.bands[k].tok0) * MSDA_D, static_cast<uint32_t>(p.bands[k].bytes), &full[s]);
-          }
-      }
-    }
-    return;
+  const int first = static_cast<int>(blockIdx.x) * 2 + grp, stride = static_cast<int>(gridDim.x) * 2;
+  const int n_my = first < nitems ? (nitems - first + stride - 1) / stride : 0;
+  const int steps_per_item = npass * p.nbands;
+  const int total = n_my * steps_per_item;                    // (item, pass, band) steps of this half
+  uint64_t* gfull = full + 2 * grp;
+  uint64_t* gempty = empty + 2 * grp;
+  const uint32_t gstage = smem_u32(ms_smem) + static_cast<uint32_t>(2 * grp) * MS_STAGE_BYTES;
+  const bool producer = gt == 0;
+  auto issue_load = [&](int t) {                              // step t of this half -> stage t & 1
+    const int item = first + (t / steps_per_item) * stride, k = t % p.nbands;
+    const int b = item / p.heads, m = item - b * p.heads;
+    const T* slab = reinterpret_cast<const T*>(p.value) + static_cast<long long>(b) * p.v_b_stride + static_cast<long long>(m) * p.S * MSDA_D;
+    mbar_arrive_expect_tx(&gfull[t & 1], static_cast<uint32_t>(p.bands[k].bytes));
+    bulk_load(ms_smem + (2 * grp + (t & 1)) * MS_STAGE_BYTES, slab + static_cast<long long>(p.bands[k].tok0) * MSDA_D, static_cast<uint32_t>(p.bands[k].bytes),
+              &gfull[t & 1]);
+  };
+  if (producer) {
+    if (total > 0) issue_load(0);
+    if (total > 1) issue_load(1);
   }
-
-  // ---------------------------------------------------------------------- consumers: thread = 8 channels of one query
-  const int ct = threadIdx.x - 32;
-  const int qi = ct >> 1, half = ct & 1;
   struct Raw {
     uint32_t off[LP];          // (dx, dy) 16-bit pairs
     uint32_t lg[LP / 2];       // logits, 16-bit pairs
     float4 ref;
   };
-  auto load_raw = [&](int item, int pass, Raw& r) {
+  auto load_raw = [&](int ip, Raw& r) {                       // ip = (item, pass) index of this half
+    if (ip >= n_my * npass) return;
+    const int item = first + (ip / npass) * stride, q = (ip % npass) * MS_QPASS + gt;
+    if (q >= p.nq) return;
     const int b = item / p.heads, m = item - b * p.heads;
-    const int q = pass * MS_QPASS + qi;
-    if (item >= nitems || q >= p.nq) return;
     const long long row = static_cast<long long>(b) * p.nq + q;
     const T* oa = reinterpret_cast<const T*>(p.offs_logits) + row * p.ld_ol;
     const uint32_t* o32 = reinterpret_cast<const uint32_t*>(oa + m * (2 * LP));
@@ -101,99 +109,119 @@ __global__ void __launch_bounds__(MS_THREADS, 1) msda_fwd_kernel(const __grid_co
     for (int i = 0; i < LP / 2; ++i) r.lg[i] = __ldg(l32 + i);
     r.ref = __ldg(reinterpret_cast<const float4*>(p.ref) + row);
   };
+  // the raw projections of the NEXT (item, pass) are prefetched while the current one is sampled - where the registers
+  // allow it (L*P <= 4: 7 registers); with 8 samples per head they are loaded on demand (once per five bands)
+  constexpr bool PREFETCH = LP <= 4;
   Raw nxt;
-  load_raw(blockIdx.x, 0, nxt);
-  uint32_t ring = 0;
-  for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+  if (PREFETCH) load_raw(0, nxt);
+  int t = 0;
+  for (int ip = 0; ip < n_my * npass; ++ip) {
+    const int item = first + (ip / npass) * stride, q = (ip % npass) * MS_QPASS + gt;
     const int b = item / p.heads, m = item - b * p.heads;
-    for (int pass = 0; pass < npass; ++pass) {
-      const int q = pass * MS_QPASS + qi;
-      const bool active = q < p.nq;
-      const Raw cur = nxt;
-      if (pass + 1 < npass) load_raw(item, pass + 1, nxt);
-      else load_raw(item + gridDim.x, 0, nxt);
-      // ---- per-(query, head) sample table: image coordinates and softmax weight (0 when the sample is outside)
-      float px[LP], py[LP], pw[LP];
-      if (active) {
-        float mx = -INFINITY;
+    const bool active = q < p.nq;
+    Raw cur;
+    if (PREFETCH) {
+      cur = nxt;
+      load_raw(ip + 1, nxt);
+    } else {
+      load_raw(ip, cur);
+    }
+    // ---- per-(query, head) sample table: image coordinates and softmax weight (0 when the sample is outside)
+    float px[LP], py[LP], pw[LP];
+    if (active) {
+      float mx = -INFINITY;
 #pragma unroll
-        for (int i = 0; i < LP / 2; ++i) {
-          const float2 f = Cvt<T>::unpack(cur.lg[i]);
-          pw[2 * i] = f.x;
-          pw[2 * i + 1] = f.y;
-          mx = fmaxf(mx, fmaxf(f.x, f.y));
-        }
-        float sum = 0.f;
-#pragma unroll
-        for (int i = 0; i < LP; ++i) {
-          pw[i] = __expf(pw[i] - mx);
-          sum += pw[i];
-        }
-        const float inv = 1.f / sum;
-        const float sx = cur.ref.z * (0.5f / NP), sy = cur.ref.w * (0.5f / NP);
-#pragma unroll
-        for (int i = 0; i < LP; ++i) {
-          const int l = i / NP;
-          const float2 o = Cvt<T>::unpack(cur.off[i]);
-          float lx = cur.ref.x + o.x * sx, ly = cur.ref.y + o.y * sy;      // ms_deform_attn.py:125-127
-          if (p.valid_ratio != nullptr) {                                  // transformer.py:352-353: boxes scaled per level
-            lx *= __ldg(p.valid_ratio + (b * NL + l) * 2);
-            ly *= __ldg(p.valid_ratio + (b * NL + l) * 2 + 1);
-          }
-          const int H = p.lvl_h[l], W = p.lvl_w[l];
-          px[i] = lx * W - 0.5f;                                           // cuh:285-286
-          py[i] = ly * H - 0.5f;
-          const bool in = py[i] > -1.f && px[i] > -1.f && py[i] < H && px[i] < W;   // cuh:288
-          pw[i] = in ? pw[i] * inv : 0.f;
-        }
+      for (int i = 0; i < LP / 2; ++i) {
+        const float2 f = Cvt<T>::unpack(cur.lg[i]);
+        pw[2 * i] = f.x;
+        pw[2 * i + 1] = f.y;
+        mx = fmaxf(mx, fmaxf(f.x, f.y));
       }
-      float acc[8];
+      float sum = 0.f;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) acc[i] = 0.f;
-      for (int k = 0; k < p.nbands; ++k, ++ring) {
-        const int s = ring % MS_STAGES;
-        const MsdaBand bd = p.bands[k];
-        mbar_wait(&full[s], (ring / MS_STAGES) & 1);
-        if (active) {
-          const uint8_t* stage = ms_smem + s * MS_STAGE_BYTES + half * 16;
+      for (int i = 0; i < LP; ++i) {
+        pw[i] = __expf(pw[i] - mx);
+        sum += pw[i];
+      }
+      const float inv = __fdividef(1.f, sum);
+      const float sx = cur.ref.z * (0.5f / NP), sy = cur.ref.w * (0.5f / NP);
 #pragma unroll
-          for (int i = 0; i < LP; ++i) {
-            if (i / NP != bd.level) continue;                              // uniform
-            const int H = p.lvl_h[i / NP], W = p.lvl_w[i / NP];
-            const float yf = floorf(py[i]), xf = floorf(px[i]);
-            const int y0 = static_cast<int>(yf), x0 = static_cast<int>(xf);
-            if (pw[i] == 0.f || y0 < bd.own0 || y0 > bd.own1) continue;
-            const float ly = py[i] - yf, lx = px[i] - xf;
-            // all four corner reads are issued unconditionally (clamped address, zero weight outside the image)
-            const int ya = max(y0, 0), yb = min(y0 + 1, H - 1), xa = max(x0, 0), xb = min(x0 + 1, W - 1);
-            const float wy0 = y0 >= 0 ? 1.f - ly : 0.f, wy1 = y0 + 1 < H ? ly : 0.f;
-            const float wx0 = x0 >= 0 ? 1.f - lx : 0.f, wx1 = x0 + 1 < W ? lx : 0.f;
-            const int ra = (ya - bd.row0) * W, rb = (yb - bd.row0) * W;
-            const U4 v00 = lds16(stage + (ra + xa) * 32), v01 = lds16(stage + (ra + xb) * 32);
-            const U4 v10 = lds16(stage + (rb + xa) * 32), v11 = lds16(stage + (rb + xb) * 32);
-            const float w00 = pw[i] * wy0 * wx0, w01 = pw[i] * wy0 * wx1, w10 = pw[i] * wy1 * wx0, w11 = pw[i] * wy1 * wx1;
-            const uint32_t u00[4] = {v00.x, v00.y, v00.z, v00.w}, u01[4] = {v01.x, v01.y, v01.z, v01.w};
-            const uint32_t u10[4] = {v10.x, v10.y, v10.z, v10.w}, u11[4] = {v11.x, v11.y, v11.z, v11.w};
+      for (int i = 0; i < LP; ++i) {
+        const int l = i / NP;
+        const float2 o = Cvt<T>::unpack(cur.off[i]);
+        float lx = cur.ref.x + o.x * sx, ly = cur.ref.y + o.y * sy;      // ms_deform_attn.py:125-127
+        if (p.valid_ratio != nullptr) {                                  // transformer.py:352-353: boxes scaled per level
+          lx *= __ldg(p.valid_ratio + (b * NL + l) * 2);
+          ly *= __ldg(p.valid_ratio + (b * NL + l) * 2 + 1);
+        }
+        const float H = static_cast<float>(p.lvl_h[l]), W = static_cast<float>(p.lvl_w[l]);
+        px[i] = lx * W - 0.5f;                                           // cuh:285-286
+        py[i] = ly * H - 0.5f;
+        const bool in = py[i] > -1.f && px[i] > -1.f && py[i] < H && px[i] < W;   // cuh:288
+        pw[i] = in ? pw[i] * inv : 0.f;
+      }
+    }
+    uint64_t acc[8];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const float2 a = Cvt<T>::unpack(u00[j]), bq = Cvt<T>::unpack(u01[j]), c = Cvt<T>::unpack(u10[j]), d = Cvt<T>::unpack(u11[j]);
-              acc[2 * j] = fmaf(w00, a.x, fmaf(w01, bq.x, fmaf(w10, c.x, fmaf(w11, d.x, acc[2 * j]))));
-              acc[2 * j + 1] = fmaf(w00, a.y, fmaf(w01, bq.y, fmaf(w10, c.y, fmaf(w11, d.y, acc[2 * j + 1]))));
+    for (int i = 0; i < 8; ++i) acc[i] = f2_pack(0.f, 0.f);
+    for (int k = 0; k < p.nbands; ++k, ++t) {
+      const int own0 = p.bands[k].own0, own1 = p.bands[k].own1, row0 = p.bands[k].row0, blvl = p.bands[k].level;
+      mbar_wait(&gfull[t & 1], (t >> 1) & 1);
+      if (active) {
+        const uint32_t stage = gstage + static_cast<uint32_t>(t & 1) * MS_STAGE_BYTES;
+#pragma unroll
+        for (int i = 0; i < LP; ++i) {
+          if (NL > 1 && i / NP != blvl) continue;                        // uniform
+          const int H = p.lvl_h[i / NP], W = p.lvl_w[i / NP];
+          const float yf = floorf(py[i]), xf = floorf(px[i]);
+          const int y0 = static_cast<int>(yf), x0 = static_cast<int>(xf);
+          if (pw[i] == 0.f || y0 < own0 || y0 > own1) continue;
+          const float ly = py[i] - yf, lx = px[i] - xf;
+          // all four corner reads are issued unconditionally (clamped address, zero weight outside the image)
+          const int ya = max(y0, 0), yb = min(y0 + 1, H - 1), xa = max(x0, 0), xb = min(x0 + 1, W - 1);
+          const float wy0 = y0 >= 0 ? pw[i] - pw[i] * ly : 0.f, wy1 = y0 + 1 < H ? pw[i] * ly : 0.f;
+          const float wx0 = x0 >= 0 ? 1.f - lx : 0.f, wx1 = x0 + 1 < W ? lx : 0.f;
+          const uint32_t ra = stage + static_cast<uint32_t>((ya - row0) * W) * 32u, rb = stage + static_cast<uint32_t>((yb - row0) * W) * 32u;
+          const uint32_t a00 = ra + xa * 32, a01 = ra + xb * 32, a10 = rb + xa * 32, a11 = rb + xb * 32;
+          const uint32_t addr[4] = {a00, a01, a10, a11};
+          const float wc[4] = {wy0 * wx0, wy0 * wx1, wy1 * wx0, wy1 * wx1};
+#pragma unroll
+          for (int rowp = 0; rowp < 2; ++rowp) {                         // the two corners of one image row at a time (16 registers in flight)
+            const U4 v[4] = {lds16(addr[rowp * 2]), lds16(addr[rowp * 2] + 16), lds16(addr[rowp * 2 + 1]), lds16(addr[rowp * 2 + 1] + 16)};
+#pragma unroll
+            for (int cx = 0; cx < 2; ++cx) {
+              const uint64_t w2 = f2_pack(wc[rowp * 2 + cx], wc[rowp * 2 + cx]);
+#pragma unroll
+              for (int hh = 0; hh < 2; ++hh) {
+                const U4 u = v[cx * 2 + hh];
+                const uint32_t uu[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const float2 f = Cvt<T>::unpack(uu[j]);
+                  acc[hh * 4 + j] = f2_fma(w2, f2_pack(f.x, f.y), acc[hh * 4 + j]);
+                }
+              }
             }
           }
         }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&empty[s]);
       }
-      if (active) {
-        U4 o;
-        o.x = Cvt<T>::pack(acc[0], acc[1]);
-        o.y = Cvt<T>::pack(acc[2], acc[3]);
-        o.z = Cvt<T>::pack(acc[4], acc[5]);
-        o.w = Cvt<T>::pack(acc[6], acc[7]);
-        const long long row = static_cast<long long>(b) * p.nq + q;
-        *reinterpret_cast<U4*>(reinterpret_cast<T*>(p.out) + row * p.ld_out + m * MSDA_D + half * 8) = o;
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&gempty[t & 1]);
+      if (producer && t + 2 < total) {                                   // re-arm this stage as soon as the whole half has left it
+        mbar_wait(&gempty[t & 1], (t >> 1) & 1);
+        issue_load(t + 2);
       }
+    }
+    if (active) {
+      U8 o;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float a0, a1;
+        f2_unpack(acc[j], a0, a1);
+        o.v[j] = Cvt<T>::pack(a0, a1);
+      }
+      const long long row = static_cast<long long>(b) * p.nq + q;
+      stg256(reinterpret_cast<T*>(p.out) + row * p.ld_out + m * MSDA_D, o);
     }
   }
 }
@@ -225,7 +253,7 @@ static int launch_fwd(const MsdaArgs& a, cudaStream_t st) {
   int e = ensure_max_dyn_smem(reinterpret_cast<const void*>(msda_fwd_kernel<T, NL, NP>), MS_SMEM);
   if (e) return e;
   const int items = a.batch * a.heads;
-  const unsigned grid = static_cast<unsigned>(std::min(items, current_device_sms()));
+  const unsigned grid = static_cast<unsigned>(std::min((items + 1) / 2, current_device_sms()));
   launch_k(msda_fwd_kernel<T, NL, NP>, dim3(grid), dim3(MS_THREADS), static_cast<size_t>(MS_SMEM), st, a);
   return static_cast<int>(cudaGetLastError());
 }

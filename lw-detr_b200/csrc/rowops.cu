@@ -15,87 +15,110 @@ namespace lwb {
 // LayerNorm of the projector on NHWC rows (projector.py:21-47) and the decoder norms (eps 1e-5).
 // Optional: rows flagged in `row_flag` take `override_vec` as input (masked two-stage memory rows,
 // transformer.py:116-123); optional second output y2 = y + add_src (decoder: tgt + query_pos).
-template <typename T, int CHUNKS>   // CHUNKS = ceil(C / 256): 8-element chunks per lane
+template <typename T, int CHUNKS, int RPW>   // CHUNKS = ceil(C / 256): 8-element chunks per lane; RPW rows per warp, loaded together
 __global__ void __launch_bounds__(256) layernorm_kernel(const LayerNormArgs p) {
   pdl_sync();   // programmatic dependent launch: release the successor, wait for the predecessor (launch.h)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const long long row = static_cast<long long>(blockIdx.x) * 8 + warp;
-  if (row >= p.rows) return;
+  const long long row0 = (static_cast<long long>(blockIdx.x) * 8 + warp) * RPW;
+  if (row0 >= p.rows) return;
   const int nchunk = p.C >> 3;
-  float v[CHUNKS][8];
-  const bool ovr = p.row_flag != nullptr && p.row_flag[row % p.flag_mod] != 0;
-  const T* x = reinterpret_cast<const T*>(p.x) + row * p.ldx;
+  float v[RPW][CHUNKS][8];
+  bool live[RPW];
+  // ---- every load of the warp's RPW rows is in flight before the first reduction (memory-level parallelism: the kernel
+  // is latency-bound, one 16-byte load per lane and row otherwise)
 #pragma unroll
-  for (int i = 0; i < CHUNKS; ++i) {
-    const int c = lane + i * 32;
-    if (c < nchunk) {
-      if (ovr) {
+  for (int r = 0; r < RPW; ++r) {
+    const long long row = row0 + r;
+    live[r] = row < p.rows;
+    const bool ovr = live[r] && p.row_flag != nullptr && p.row_flag[row % p.flag_mod] != 0;
+    const T* x = reinterpret_cast<const T*>(p.x) + (live[r] ? row : row0) * p.ldx;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) v[i][j] = p.override_vec[c * 8 + j];
+    for (int i = 0; i < CHUNKS; ++i) {
+      const int c = lane + i * 32;
+      if (c < nchunk) {
+        if (ovr) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[r][i][j] = p.override_vec[c * 8 + j];
+        } else {
+          const U4 u = *reinterpret_cast<const U4*>(x + c * 8);
+          const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float2 f = Cvt<T>::unpack(w4[j]);
+            v[r][i][2 * j] = f.x;
+            v[r][i][2 * j + 1] = f.y;
+          }
+        }
       } else {
-        const U4 u = *reinterpret_cast<const U4*>(x + c * 8);
-        const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float2 f = Cvt<T>::unpack(w4[j]);
-          v[i][2 * j] = f.x;
-          v[i][2 * j + 1] = f.y;
-        }
-      }
-    } else {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) v[i][j] = 0.f;
-    }
-  }
-  float s = 0.f;
-#pragma unroll
-  for (int i = 0; i < CHUNKS; ++i)
-#pragma unroll
-    for (int j = 0; j < 8; ++j) s += v[i][j];
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-  const float mean = s / p.C;
-  float q = 0.f;
-#pragma unroll
-  for (int i = 0; i < CHUNKS; ++i) {
-    if (lane + i * 32 < nchunk) {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float d = v[i][j] - mean;
-        q += d * d;
+        for (int j = 0; j < 8; ++j) v[r][i][j] = 0.f;
       }
     }
   }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
-  const float rstd = rsqrtf(q / p.C + p.eps);
-  const long long yrow = p.y_group > 0 ? (row / p.y_group) * p.y_group_stride + p.y_row_off + row % p.y_group : row;
-  T* y = reinterpret_cast<T*>(p.y) + yrow * p.ldy;
+  float wv[CHUNKS][8], bv[CHUNKS][8];
 #pragma unroll
   for (int i = 0; i < CHUNKS; ++i) {
     const int c = lane + i * 32;
-    if (c < nchunk) {
-      float r[8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) r[j] = (v[i][j] - mean) * rstd * __ldg(p.w + c * 8 + j) + __ldg(p.b + c * 8 + j);
-      U4 o;
-      o.x = Cvt<T>::pack(r[0], r[1]); o.y = Cvt<T>::pack(r[2], r[3]);
-      o.z = Cvt<T>::pack(r[4], r[5]); o.w = Cvt<T>::pack(r[6], r[7]);
-      *reinterpret_cast<U4*>(y + c * 8) = o;
-      if (p.y2 != nullptr) {
-        const T* a = reinterpret_cast<const T*>(p.add_src) + row * p.ld_add + c * 8;
-        const U4 u = *reinterpret_cast<const U4*>(a);
-        const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
-        uint32_t o2[4];
+    for (int j = 0; j < 8; ++j) {
+      wv[i][j] = c < nchunk ? __ldg(p.w + c * 8 + j) : 0.f;
+      bv[i][j] = c < nchunk ? __ldg(p.b + c * 8 + j) : 0.f;
+    }
+  }
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float2 f = Cvt<T>::unpack(w4[j]);
-          // add to the ROUNDED y so that y2 == y + add exactly as a 16-bit consumer would compute it
-          const float2 yr = Cvt<T>::unpack(j == 0 ? o.x : j == 1 ? o.y : j == 2 ? o.z : o.w);
-          o2[j] = Cvt<T>::pack(yr.x + f.x, yr.y + f.y);
+  for (int r = 0; r < RPW; ++r) {
+    if (!live[r]) continue;
+    const long long row = row0 + r;
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < CHUNKS; ++i)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s += v[r][i][j];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float mean = s / p.C;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < CHUNKS; ++i) {
+      if (lane + i * 32 < nchunk) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float d = v[r][i][j] - mean;
+          q += d * d;
         }
-        U4 oo; oo.x = o2[0]; oo.y = o2[1]; oo.z = o2[2]; oo.w = o2[3];
-        *reinterpret_cast<U4*>(reinterpret_cast<T*>(p.y2) + row * p.ldy2 + c * 8) = oo;
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+    const float rstd = rsqrtf(q / p.C + p.eps);
+    const long long yrow = p.y_group > 0 ? (row / p.y_group) * p.y_group_stride + p.y_row_off + row % p.y_group : row;
+    T* y = reinterpret_cast<T*>(p.y) + yrow * p.ldy;
+#pragma unroll
+    for (int i = 0; i < CHUNKS; ++i) {
+      const int c = lane + i * 32;
+      if (c < nchunk) {
+        float o8[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o8[j] = (v[r][i][j] - mean) * rstd * wv[i][j] + bv[i][j];
+        U4 o;
+        o.x = Cvt<T>::pack(o8[0], o8[1]); o.y = Cvt<T>::pack(o8[2], o8[3]);
+        o.z = Cvt<T>::pack(o8[4], o8[5]); o.w = Cvt<T>::pack(o8[6], o8[7]);
+        *reinterpret_cast<U4*>(y + c * 8) = o;
+        if (p.y2 != nullptr) {
+          const T* a = reinterpret_cast<const T*>(p.add_src) + row * p.ld_add + c * 8;
+          const U4 u = *reinterpret_cast<const U4*>(a);
+          const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
+          uint32_t o2[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float2 f = Cvt<T>::unpack(w4[j]);
+            // add to the ROUNDED y so that y2 == y + add exactly as a 16-bit consumer would compute it
+            const float2 yr = Cvt<T>::unpack(j == 0 ? o.x : j == 1 ? o.y : j == 2 ? o.z : o.w);
+            o2[j] = Cvt<T>::pack(yr.x + f.x, yr.y + f.y);
+          }
+          U4 oo; oo.x = o2[0]; oo.y = o2[1]; oo.z = o2[2]; oo.w = o2[3];
+          *reinterpret_cast<U4*>(reinterpret_cast<T*>(p.y2) + row * p.ldy2 + c * 8) = oo;
+        }
       }
     }
   }
@@ -103,12 +126,14 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const LayerNormArgs p) {
 
 template <typename T>
 static int ln_dispatch(const LayerNormArgs& a, cudaStream_t st) {
-  const unsigned grid = static_cast<unsigned>((a.rows + 7) / 8);
   const int chunks = (a.C + 255) / 256;
-  if (chunks == 1) launch_k(layernorm_kernel<T, 1>, dim3(grid), dim3(256), 0, st, a);
-  else if (chunks == 2) launch_k(layernorm_kernel<T, 2>, dim3(grid), dim3(256), 0, st, a);
-  else if (chunks == 3) launch_k(layernorm_kernel<T, 3>, dim3(grid), dim3(256), 0, st, a);
-  else if (chunks == 4) launch_k(layernorm_kernel<T, 4>, dim3(grid), dim3(256), 0, st, a);
+  // rows per warp: 4 when there are enough rows to keep every SM busy with a quarter of the warps, else 1
+  const bool many = a.rows >= 8LL * 4 * 2 * current_device_sms();
+  const unsigned grid4 = static_cast<unsigned>((a.rows + 31) / 32), grid1 = static_cast<unsigned>((a.rows + 7) / 8);
+  if (chunks == 1) { if (many) launch_k(layernorm_kernel<T, 1, 4>, dim3(grid4), dim3(256), 0, st, a); else launch_k(layernorm_kernel<T, 1, 1>, dim3(grid1), dim3(256), 0, st, a); }
+  else if (chunks == 2) { if (many) launch_k(layernorm_kernel<T, 2, 4>, dim3(grid4), dim3(256), 0, st, a); else launch_k(layernorm_kernel<T, 2, 1>, dim3(grid1), dim3(256), 0, st, a); }
+  else if (chunks == 3) launch_k(layernorm_kernel<T, 3, 1>, dim3(grid1), dim3(256), 0, st, a);
+  else if (chunks == 4) launch_k(layernorm_kernel<T, 4, 1>, dim3(grid1), dim3(256), 0, st, a);
   else return -2;
   return static_cast<int>(cudaGetLastError());
 }
@@ -474,9 +499,11 @@ __global__ void __launch_bounds__(256) query_init_kernel(const float* __restrict
     const int coord_slot = i / dim;             // output order (y, x, w, h)
     const int e = i % dim;
     const float c = rp[coord_slot == 0 ? 1 : (coord_slot == 1 ? 0 : coord_slot)];
-    const float dim_t = powf(10000.f, static_cast<float>(2 * (e / 2)) / static_cast<float>(dim));
-    const float v = c * two_pi / dim_t;
-    sine[row * (2 * d) + i] = Cvt<T>::from_f((e & 1) ? cosf(v) : sinf(v));
+    // 1 / dim_t = 10000^(-2*(e/2)/dim) by exp2 (13.2877 = log2 1e4); |v| <= 2*pi*1.2: the fast sin/cos are exact to ~1e-6 there,
+    // far below the 16-bit rounding of the embedding
+    const float inv_dim_t = exp2f(-13.287712379549449f * static_cast<float>(2 * (e / 2)) / static_cast<float>(dim));
+    const float v = c * two_pi * inv_dim_t;
+    sine[row * (2 * d) + i] = Cvt<T>::from_f((e & 1) ? __cosf(v) : __sinf(v));
   }
 }
 int query_init_launch(int dtype, const float* delta_ts, const float* proposals, const int* idx, const float* refpoint_embed, int B,

@@ -22,14 +22,15 @@ __device__ __forceinline__ uint32_t pack_h2(float a, float b) { __half2 h = __fl
 static constexpr float MAGIC = 12582912.f;   // 1.5 * 2^23
 
 // exp2 of the pair (s.x*c - m, s.y*c - m) without the MUFU
-__device__ __forceinline__ void exp2_poly_pair(uint64_t s2, uint64_t c2, uint64_t magic_minus_m2, uint64_t negm2, float& e0, float& e1) {
+// (the scores are clamped from below first: an argument under -126 would leave the fraction outside the polynomial's range)
+__device__ __forceinline__ void exp2_poly_pair(uint64_t s2in, uint64_t c2, uint64_t magic_minus_m2, uint64_t negm2, float& e0, float& e1) {
+  float s0, s1;
+  upk2(s2in, s0, s1);
+  const uint64_t s2 = pk2(fmaxf(s0, -300.f), fmaxf(s1, -300.f));
   const uint64_t t2 = fma2(s2, c2, magic_minus_m2);          // round(s*c - m) + MAGIC
   float t0, t1;
   upk2(t2, t0, t1);
-  t0 = fmaxf(t0, MAGIC - 126.f);
-  t1 = fmaxf(t1, MAGIC - 126.f);
-  const uint64_t tc2 = pk2(t0, t1);
-  const uint64_t r2 = add2(tc2, pk2(-MAGIC, -MAGIC));        // the integer part
+  const uint64_t r2 = add2(t2, pk2(-MAGIC, -MAGIC));         // the integer part
   const uint64_t u2 = fma2(r2, pk2(-1.f, -1.f), negm2);      // -m - r
   const uint64_t f2 = fma2(s2, c2, u2);                      // fraction in [-0.5, 0.5]
   uint64_t p2 = fma2(f2, pk2(0.05517164617776871f, 0.05517164617776871f), pk2(0.2426111251115799f, 0.2426111251115799f));
