@@ -70,19 +70,23 @@ static constexpr int NSTAGE = 3;   // K/V ring: chunk ch+2 is prefetched while c
 // One 64-key chunk of the online-softmax attention for a warp's 16 query rows.
 //   qf: Q fragments (A operand); cK / cV: the chunk's K and V rows in shared memory ([64][LDS]);
 //   kbase: index of the chunk's first key; keys >= seqlen are masked.
-template <typename T, int DH>
+//   PM: bit nt set = the exponentials of n-tile nt take the polynomial exp2 on the FMA pipe (ptx.cuh) instead of the MUFU.
+//   NT: 8-key n-tiles of this chunk that can hold valid keys (8 = the full 64-key chunk; the second chunk of a 100-token
+//       window only needs 5: no scores, exponentials or P V steps are spent on keys that cannot exist).
+template <typename T, int DH, uint32_t PM = 0, int NT = 8>
 __device__ __forceinline__ void attn_chunk(const uint32_t (&qf)[DH / 16][4], const T* cK, const T* cV, int kbase, int seqlen,
-                                           float scale_log2, int lane, float (&m_run)[2], float (&lsum)[4],
+                                           float scale_log2, float inv_scale_log2, int lane, float (&m_run)[2], float (&lsum)[4],
                                            float (&o)[DH / 8][4]) {
   constexpr int LDS = DH + 8;
   const int t4 = lane & 3;
   const uint32_t ones2 = Cvt<T>::pack(1.f, 1.f);
     // ---- S = Q K^T for 64 keys: 8 n-tiles of 8 keys
-    float s[KC / 8][4];
+    constexpr int NTP = (NT + 1) & ~1;   // n-tiles are produced in pairs (one ldmatrix.x4 feeds two)
+    float s[NTP][4];
 #pragma unroll
-    for (int nt = 0; nt < KC / 8; ++nt) s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
+    for (int nt = 0; nt < NTP; ++nt) s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
 #pragma unroll
-    for (int nt = 0; nt < KC / 8; nt += 2) {
+    for (int nt = 0; nt < NTP; nt += 2) {
 #pragma unroll
       for (int kk = 0; kk < DH / 16; ++kk) {
         // x4 = (keys nt*8.., dh lo), (keys nt*8.., dh hi), (keys (nt+1)*8.., dh lo), (keys (nt+1)*8.., dh hi)
@@ -97,16 +101,16 @@ __device__ __forceinline__ void attn_chunk(const uint32_t (&qf)[DH / 16][4], con
     // ---- online softmax.  Instruction diet (the kernel is MUFU/issue bound at dh = 16): the max runs on the
     // raw scores, scale and max-subtraction are one FFMA feeding ex2, tail masking only touches the last
     // chunk, and the row sums come from one extra MMA against a ones fragment (below) instead of FADDs.
-    if (kbase + KC > seqlen) {
+    if (kbase + NT * 8 > seqlen) {
 #pragma unroll
-      for (int nt = 0; nt < KC / 8; ++nt)
+      for (int nt = 0; nt < NT; ++nt)
 #pragma unroll
         for (int j = 0; j < 4; ++j)
           if (kbase + nt * 8 + t4 * 2 + (j & 1) >= seqlen) s[nt][j] = -INFINITY;
     }
     float mx[2] = {-INFINITY, -INFINITY};
 #pragma unroll
-    for (int nt = 0; nt < KC / 8; ++nt) {
+    for (int nt = 0; nt < NT; ++nt) {
       mx[0] = fmaxf(mx[0], fmaxf(s[nt][0], s[nt][1]));
       mx[1] = fmaxf(mx[1], fmaxf(s[nt][2], s[nt][3]));
     }
@@ -120,13 +124,26 @@ __device__ __forceinline__ void attn_chunk(const uint32_t (&qf)[DH / 16][4], con
       m_run[h] = m_new;
       msc[h] = m_new * scale_log2;
     }
-    uint32_t pf[KC / 16][4];
+    uint32_t pf[NTP / 2][4];
+    const uint64_t c2 = f2_pack(scale_log2, scale_log2);
 #pragma unroll
-    for (int nt = 0; nt < KC / 8; ++nt) {
-      const float p0 = fast_exp2(fmaf(s[nt][0], scale_log2, -msc[0]));
-      const float p1 = fast_exp2(fmaf(s[nt][1], scale_log2, -msc[0]));
-      const float p2 = fast_exp2(fmaf(s[nt][2], scale_log2, -msc[1]));
-      const float p3 = fast_exp2(fmaf(s[nt][3], scale_log2, -msc[1]));
+    for (int nt = 0; nt < NTP; ++nt) {
+      if (nt >= NT) {                                          // padding half of the last 16-key step
+        pf[nt >> 1][(nt & 1) * 2 + 0] = 0u;
+        pf[nt >> 1][(nt & 1) * 2 + 1] = 0u;
+        continue;
+      }
+      float p0, p1, p2, p3;
+      if ((PM >> nt) & 1u) {
+        constexpr float kMagic = 12582912.f;
+        exp2_poly2(s[nt][0], s[nt][1], m_run[0] - 125.f * inv_scale_log2, c2, f2_pack(kMagic - msc[0], kMagic - msc[0]), f2_pack(-msc[0], -msc[0]), p0, p1);
+        exp2_poly2(s[nt][2], s[nt][3], m_run[1] - 125.f * inv_scale_log2, c2, f2_pack(kMagic - msc[1], kMagic - msc[1]), f2_pack(-msc[1], -msc[1]), p2, p3);
+      } else {
+        p0 = fast_exp2(fmaf(s[nt][0], scale_log2, -msc[0]));
+        p1 = fast_exp2(fmaf(s[nt][1], scale_log2, -msc[0]));
+        p2 = fast_exp2(fmaf(s[nt][2], scale_log2, -msc[1]));
+        p3 = fast_exp2(fmaf(s[nt][3], scale_log2, -msc[1]));
+      }
       // C fragments of n-tiles (2j, 2j+1) form the A fragment of key-step j
       pf[nt >> 1][(nt & 1) * 2 + 0] = Cvt<T>::pack(p0, p1);
       pf[nt >> 1][(nt & 1) * 2 + 1] = Cvt<T>::pack(p2, p3);
@@ -142,7 +159,7 @@ __device__ __forceinline__ void attn_chunk(const uint32_t (&qf)[DH / 16][4], con
     }
     // ---- O += P V
 #pragma unroll
-    for (int kt = 0; kt < KC / 16; ++kt) {
+    for (int kt = 0; kt < NTP / 2; ++kt) {
       Mma<T>::run(lsum, pf[kt], ones2, ones2);               // row sums of the rounded P, fp32 accumulate
 #pragma unroll
       for (int dt = 0; dt < DH / 8; dt += 2) {
@@ -157,7 +174,7 @@ __device__ __forceinline__ void attn_chunk(const uint32_t (&qf)[DH / 16][4], con
     }
 }
 
-template <typename T, int DH, int WARPS>
+template <typename T, int DH, int WARPS, uint32_t PM = 0>
 __global__ void __launch_bounds__(WARPS * 32) attn_kernel(const AttnArgs p) {
   pdl_sync();   // programmatic dependent launch: release the successor, wait for the predecessor (launch.h)
   constexpr int QROWS = WARPS * 16;
@@ -225,7 +242,7 @@ __global__ void __launch_bounds__(WARPS * 32) attn_kernel(const AttnArgs p) {
     const T* cK = sK + buf * KC * LDS;
     const T* cV = sV + buf * KC * LDS;
 
-    attn_chunk<T, DH>(qf, cK, cV, ch * KC, p.seqlen, p.scale_log2, lane, m_run, lsum, o);
+    attn_chunk<T, DH, PM>(qf, cK, cV, ch * KC, p.seqlen, p.scale_log2, 1.f / p.scale_log2, lane, m_run, lsum, o);
   }
 
   // ---- finalise: divide by the row sums, stage through this warp's Q rows, 16-byte coalesced stores
@@ -254,7 +271,7 @@ __global__ void __launch_bounds__(WARPS * 32) attn_kernel(const AttnArgs p) {
 // running at the same time read neighbouring 32..128-byte slices of the same token rows) and prefetch item
 // i+2 into a 3-deep buffer ring while item i is computed - the HBM latency is hidden behind the math and the
 // kernel runs at the larger of its HBM time and its exp (MUFU) time.
-template <typename T, int DH>
+template <typename T, int DH, uint32_t PM = 0>
 __global__ void __launch_bounds__(7 * 32) attn_short_kernel(const AttnArgs p) {
   pdl_sync();   // programmatic dependent launch: release the successor, wait for the predecessor (launch.h)
   constexpr int WARPS = 7, QROWS = 112, KROWS = 128, NBUF = 3;
@@ -313,8 +330,10 @@ __global__ void __launch_bounds__(7 * 32) attn_short_kernel(const AttnArgs p) {
     for (int i = 0; i < DH / 8; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
     float m_run[2] = {-INFINITY, -INFINITY};
     float lsum[4] = {0.f, 0.f, 0.f, 0.f};
-    attn_chunk<T, DH>(qf, sK, sV, 0, p.seqlen, p.scale_log2, lane, m_run, lsum, o);
-    if (p.seqlen > KC) attn_chunk<T, DH>(qf, sK + KC * LDS, sV + KC * LDS, KC, p.seqlen, p.scale_log2, lane, m_run, lsum, o);
+    const float inv_c = 1.f / p.scale_log2;
+    attn_chunk<T, DH, PM>(qf, sK, sV, 0, p.seqlen, p.scale_log2, inv_c, lane, m_run, lsum, o);
+    if (p.seqlen > KC + 40) attn_chunk<T, DH, PM, 6>(qf, sK + KC * LDS, sV + KC * LDS, KC, p.seqlen, p.scale_log2, inv_c, lane, m_run, lsum, o);   // keys 64..111 (seqlen <= 112 here)
+    else if (p.seqlen > KC) attn_chunk<T, DH, PM, 5>(qf, sK + KC * LDS, sV + KC * LDS, KC, p.seqlen, p.scale_log2, inv_c, lane, m_run, lsum, o);   // keys 64..103: the 100-token windows
 
     const float l_run[2] = {1.f / lsum[0], 1.f / lsum[2]};
     T* sO = sQ + warp * 16 * LDS;          // this warp's own Q rows: already consumed into qf
@@ -337,44 +356,60 @@ __global__ void __launch_bounds__(7 * 32) attn_short_kernel(const AttnArgs p) {
   }
 }
 
-template <typename T, int DH>
+template <typename T, int DH, uint32_t PM = 0>
 static int launch_short(const AttnArgs& a, cudaStream_t st) {
   constexpr int LDS = DH + 8;
   const size_t smem = static_cast<size_t>(3) * (112 + 256) * LDS * sizeof(T);
-  if (int e = ensure_max_dyn_smem(reinterpret_cast<const void*>(attn_short_kernel<T, DH>), 200 * 1024)) return e;
+  if (int e = ensure_max_dyn_smem(reinterpret_cast<const void*>(attn_short_kernel<T, DH, PM>), 200 * 1024)) return e;
   static int ctas_per_sm = 0;   // a property of the kernel image and the sm_100a SM, identical on every device of a B200 box
   if (!ctas_per_sm) {
     int n = 0;
-    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, attn_short_kernel<T, DH>, 7 * 32, smem);
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, attn_short_kernel<T, DH, PM>, 7 * 32, smem);
     if (e != cudaSuccess) return static_cast<int>(e);
     ctas_per_sm = n > 0 ? n : 1;
   }
   const int sms = current_device_sms();
   const long long items = static_cast<long long>(a.nseq) * a.heads;
   const unsigned grid = static_cast<unsigned>(std::min<long long>(items, static_cast<long long>(sms) * ctas_per_sm));
-  launch_k(attn_short_kernel<T, DH>, dim3(grid), dim3(7 * 32), smem, st, a);
+  launch_k(attn_short_kernel<T, DH, PM>, dim3(grid), dim3(7 * 32), smem, st, a);
   return static_cast<int>(cudaGetLastError());
 }
 
-template <typename T, int DH, int WARPS>
+template <typename T, int DH, int WARPS, uint32_t PM = 0>
 static int launch(const AttnArgs& a, cudaStream_t st) {
   constexpr int LDS = DH + 8;
   const size_t smem = static_cast<size_t>(WARPS * 16 + 2 * NSTAGE * KC) * LDS * sizeof(T);
-  if (int e = ensure_max_dyn_smem(reinterpret_cast<const void*>(attn_kernel<T, DH, WARPS>), 96 * 1024)) return e;
+  if (int e = ensure_max_dyn_smem(reinterpret_cast<const void*>(attn_kernel<T, DH, WARPS, PM>), 96 * 1024)) return e;
   dim3 grid((a.seqlen + WARPS * 16 - 1) / (WARPS * 16), a.heads, a.nseq);
-  launch_k(attn_kernel<T, DH, WARPS>, dim3(grid), dim3(WARPS * 32), smem, st, a);
+  launch_k(attn_kernel<T, DH, WARPS, PM>, dim3(grid), dim3(WARPS * 32), smem, st, a);
   return static_cast<int>(cudaGetLastError());
+}
+
+// Share of the exponentials that takes the polynomial exp2 (FMA pipe) instead of the MUFU in the mma.sync kernels at
+// head dims 16 / 32, where the MUFU is the roof: 0 = none, 1 = 2 of 8 n-tiles, 2 = 3 of 8.  LWDETR_B200_ATTN_POLY
+// overrides the default for A/B measurements.
+static int poly_policy() {
+  static int v = [] {
+    const char* e = getenv("LWDETR_B200_ATTN_POLY");
+    return e ? atoi(e) : 0;
+  }();
+  return v;
 }
 
 template <typename T>
 static int dispatch(const AttnArgs& a, int dh, cudaStream_t st) {
+  const int pol = poly_policy();
   if (a.seqlen <= 112) {
-    if (dh == 16) return launch_short<T, 16>(a, st);
-    if (dh == 32) return launch_short<T, 32>(a, st);
+    if (dh == 16) return pol == 1 ? launch_short<T, 16, 0x24u>(a, st) : pol == 2 ? launch_short<T, 16, 0x49u>(a, st) : launch_short<T, 16>(a, st);
+    if (dh == 32) return pol == 1 ? launch_short<T, 32, 0x24u>(a, st) : pol == 2 ? launch_short<T, 32, 0x49u>(a, st) : launch_short<T, 32>(a, st);
     if (dh == 64) return launch_short<T, 64>(a, st);
     return -2;
   }
   const int warps = a.seqlen >= 1024 ? 8 : 4;
+  if (warps == 8 && pol > 0) {
+    if (dh == 16) return pol == 1 ? launch<T, 16, 8, 0x24u>(a, st) : launch<T, 16, 8, 0x49u>(a, st);
+    if (dh == 32) return pol == 1 ? launch<T, 32, 8, 0x24u>(a, st) : launch<T, 32, 8, 0x49u>(a, st);
+  }
 #define LWB_ATTN_CASE(D, W) if (dh == D && warps == W) return launch<T, D, W>(a, st);
   LWB_ATTN_CASE(16, 8) LWB_ATTN_CASE(16, 4)
   LWB_ATTN_CASE(32, 8) LWB_ATTN_CASE(32, 4)

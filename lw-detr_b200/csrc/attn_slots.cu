@@ -44,7 +44,8 @@ namespace sl {
 static constexpr int SLOTS = 4;
 static constexpr int BM = 128;                 // query rows per slot
 static constexpr int BK = 64;                  // keys per chunk
-static constexpr int THREADS = 32 * (SLOTS + 4 * SLOTS);
+static constexpr int W_DRIVER = 4 * SLOTS;      // warps 0-15: softmax (slot = warp / 4, TMEM lane quarter = warp % 4); 16-19: one driver per slot
+static constexpr int THREADS = 32 * (W_DRIVER + SLOTS);
 static constexpr float LAZY_LOG2 = 8.f;        // the row reference maximum moves only when exceeded by more than 2^8
 static constexpr float MAGIC = 12582912.f;     // 1.5 * 2^23
 
@@ -52,6 +53,17 @@ __device__ __forceinline__ uint64_t desc(uint32_t smem_addr, uint32_t sbo_bytes,
   uint64_t d = 0;
   d |= static_cast<uint64_t>((smem_addr >> 4) & 0x3FFFu);
   d |= static_cast<uint64_t>(1) << 16;
+  d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFFu) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(layout_type) << 61;
+  return d;
+}
+// same with an explicit leading byte offset: for an MN-major operand that is the distance between two 16-element
+// (32-byte) atoms along N - used to append a constant block of ones to the V tile (fused row sums, see FUSED below)
+__device__ __forceinline__ uint64_t desc_lbo(uint32_t smem_addr, uint32_t sbo_bytes, uint32_t layout_type, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr >> 4) & 0x3FFFu);
+  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFFu) << 16;
   d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFFu) << 32;
   d |= static_cast<uint64_t>(1) << 46;
   d |= static_cast<uint64_t>(layout_type) << 61;
@@ -148,16 +160,41 @@ struct WaitDbg {
   unsigned int n;
   unsigned int rec[64][4];
 };
-__device__ __forceinline__ void wait_tag(uint64_t* bar, uint32_t parity, WaitDbg* dbg, int tag) {
-  if (dbg == nullptr) {
-    mbar_wait(bar, parity);
-    return;
-  }
-  if (mbar_try_wait(bar, parity)) return;
-  const long long t0 = clock64();
-  while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 100000000LL) {
-      if ((threadIdx.x & 31) == 0 || true) {
+
+// Barrier operations on precomputed 32-bit shared addresses: the generic-pointer forms re-derive the address (cvta, CTA-id
+// mapping, alignment arithmetic) at every use when registers are tight - ncu counted ~115 of 400 instructions per chunk of a
+// softmax thread in synchronisation code that should be a dozen.
+__device__ __forceinline__ bool try_wait_a(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ bool test_a(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a pipeline bug must surface as a trap (CUDA error), never as a hung GPU.  The spin is try_wait + counter +
+// branch (try_wait itself suspends the thread for a while); after 2^26 failed tries (>= 0.5 s) the thread traps, leaving a
+// record (source line, CTA, thread, parity) in mapped host memory when the debug buffer exists.
+__device__ __forceinline__ void wait_a(uint32_t bar, uint32_t parity, WaitDbg* dbg, int tag) {
+  if (try_wait_a(bar, parity)) return;
+  uint32_t spins = 0;
+  while (!try_wait_a(bar, parity)) {
+    if (++spins > (dbg != nullptr ? (1u << 21) : (1u << 26))) {
+      if (dbg != nullptr) {
         const unsigned i = atomicAdd(&dbg->n, 1u);
         if (i < 64) {
           dbg->rec[i][0] = static_cast<unsigned>(tag);
@@ -171,7 +208,21 @@ __device__ __forceinline__ void wait_tag(uint64_t* bar, uint32_t parity, WaitDbg
     }
   }
 }
-#define SL_WAIT(bar, par) wait_tag(bar, par, p.dbg, __LINE__)
+__device__ __forceinline__ void arrive_a(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
+__device__ __forceinline__ void expect_tx_a(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void commit_a(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tma_2d_a(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+
+#define SL_WAIT(bar, par) wait_a(bar, par, p.dbg, __LINE__)
 
 struct SlotArgs {
   WaitDbg* dbg;
@@ -200,7 +251,7 @@ struct Geo {
   static constexpr uint32_t SLOT_COLS = 128;                   // S 64 | P 32 | O DH (<= 32): four slots fill the 512 columns
 };
 
-template <typename T, int DH, bool SHARED, uint32_t PMASK>
+template <typename T, int DH, bool SHARED, uint32_t PMASK, bool FUSED>
 __global__ void __launch_bounds__(THREADS, 1) attn_slots_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
                                                                 const SlotArgs p) {
   using G = Geo<DH, SHARED>;
@@ -213,7 +264,11 @@ __global__ void __launch_bounds__(THREADS, 1) attn_slots_kernel(const __grid_con
   // tile of ones, four extra N = 16 MMAs per chunk on a pipe that is ~10 % busy) instead of one FADD2 per pair in the
   // softmax threads, whose instruction stream is what bounds the kernel; l is then the sum of the ROUNDED P, exactly what
   // the P V product sees.  At head dim 32 the columns are taken by O and the sums stay in registers.
+  // FUSED: the ones are appended to the V tile instead - the B operand of O += P V becomes [V | 1] with N = 32 (second
+  // MN atom = the ones block, reached through the descriptor's leading byte offset), so the SAME four MMAs per chunk
+  // produce O in columns 96-111 and the row sums in columns 112-127 (a tcgen05.mma costs the same ~45 clk for any N <= 64).
   constexpr bool SUMS = DH == 16;
+  static_assert(!FUSED || SUMS, "fused row sums need the 16 spare TMEM columns of head dim 16");
   extern __shared__ uint8_t sl_smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(sl_smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = smem;                                          // [slot][2][Q_BYTES]
@@ -254,12 +309,12 @@ __global__ void __launch_bounds__(THREADS, 1) attn_slots_kernel(const __grid_con
     }
     fence_mbar_init();
   }
-  if (warp == 0) {
+  if (warp == W_DRIVER) {
     tmem_alloc(tmem_slot, 512);
     tmem_relinquish();
   }
-  if (SUMS && threadIdx.x >= 32 && threadIdx.x < 32 + 128) {
-    reinterpret_cast<uint32_t*>(sOnes)[threadIdx.x - 32] = Cvt<T>::pack(1.f, 1.f);
+  if (SUMS && threadIdx.x < 128) {
+    reinterpret_cast<uint32_t*>(sOnes)[threadIdx.x] = Cvt<T>::pack(1.f, 1.f);
     fence_proxy_async_smem();                                    // generic-proxy writes -> visible to the tensor core's reads
   }
   tc_fence_before();
@@ -267,20 +322,22 @@ __global__ void __launch_bounds__(THREADS, 1) attn_slots_kernel(const __grid_con
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
   pdl_sync();   // the prologue above touched no global data; everything below reads the predecessor's output
+  // 32-bit shared addresses of the barrier arrays (8 bytes per barrier)
+  const uint32_t a_bars = smem_u32(bars);
+  const uint32_t a_q_full = a_bars, a_q_empty = a_q_full + 16 * SLOTS, a_s_full = a_q_empty + 16 * SLOTS, a_s_free = a_s_full + 8 * SLOTS;
+  const uint32_t a_p_full = a_s_free + 8 * SLOTS, a_p_empty = a_p_full + 8 * SLOTS, a_o_full = a_p_empty + 8 * SLOTS, a_o_free = a_o_full + 8 * SLOTS;
+  const uint32_t a_kv_full = a_o_free + 8 * SLOTS, a_kv_empty = a_kv_full + 8 * G::NRINGS * STAGES;
 
-  const int slot = warp < SLOTS ? warp : (warp - SLOTS) >> 2;
   const int nchunks = (p.seqlen + BK - 1) / BK;
   const int sh_total = p.nseq * p.heads;
-  const int first = SHARED ? static_cast<int>(blockIdx.x) : static_cast<int>(blockIdx.x) * SLOTS + slot;
-  const int stride = SHARED ? static_cast<int>(gridDim.x) : static_cast<int>(gridDim.x) * SLOTS;
-  // item -> (sequence, head, query tile of this slot); false when the slot idles during this item
-  auto decode = [&](int item, int& seq, int& head, int& qtile) -> bool {
+  // item -> (sequence, head, query tile of slot sl); false when that slot idles during this item
+  auto decode = [&](int item, int sl, int& seq, int& head, int& qtile) -> bool {
     if (SHARED) {
       const int g = item / sh_total, sh = item - g * sh_total;
       seq = sh / p.heads;
       head = sh - seq * p.heads;
       const int t0 = g * p.qtiles / p.ngroups, t1 = (g + 1) * p.qtiles / p.ngroups;
-      qtile = t0 + slot;
+      qtile = t0 + sl;
       return qtile < t1;
     }
     qtile = item % p.qtiles;
@@ -289,96 +346,145 @@ __global__ void __launch_bounds__(THREADS, 1) attn_slots_kernel(const __grid_con
     seq = sh / p.heads;
     return true;
   };
-  const uint32_t tslot = tmem + static_cast<uint32_t>(slot) * G::SLOT_COLS;
+  // CTA items (SHARED) / slot items (independent slots) of slot sl: first, first + stride, ...
+  auto first_of = [&](int sl) { return SHARED ? static_cast<int>(blockIdx.x) : static_cast<int>(blockIdx.x) * SLOTS + sl; };
+  const int stride = SHARED ? static_cast<int>(gridDim.x) : static_cast<int>(gridDim.x) * SLOTS;
+  auto count_of = [&](int sl) { const int f = first_of(sl); return f < p.nitems ? (p.nitems - f + stride - 1) / stride : 0; };
 
-  if (warp < SLOTS) {
+  if (warp >= W_DRIVER) {
     reg_dec<64>();
     if (lane == 0) {
-      // -------------------------------------------------------------------- driver of one slot: TMA + tcgen05.mma
+      // ---------------------------------------------------------------- driver of one slot: its tcgen05.mma, its TMA loads.
+      // The slot's work is a flat stream of (item, chunk) steps; S is issued one chunk ahead of the softmax warps, P V follows
+      // them, loads run ahead as far as the ring allows (non-blocking probe).  This thread's own instruction stream is the
+      // critical path of the slot - ncu of the first version (profiles/r02h_ncu_glb_small.txt) showed the softmax warps
+      // waiting for S a quarter of their time while the lone driver thread worked through ~250 instructions per chunk at
+      // one dependent instruction per 10-20 clocks - so everything per chunk is incremental: no divisions, no descriptor
+      // rebuilds, stage / phase counters that wrap by comparison.  With the shared ring the four drivers take turns at the
+      // K/V fills (fill f belongs to driver f mod 4).
+      const int slot = warp - W_DRIVER;
+      const uint32_t tslot = tmem + static_cast<uint32_t>(slot) * G::SLOT_COLS;
       constexpr bool BF = Cvt<T>::is_bf16;
       constexpr uint32_t idesc_s = umma_idesc_f16(BF, BM, BK);                 // S: N = 64 keys, Q and K both K-major
-      constexpr uint32_t idesc_o = umma_idesc_f16(BF, BM, DH) | (1u << 16);    // O: B (= V) is MN-major
+      constexpr uint32_t idesc_o = umma_idesc_f16(BF, BM, FUSED ? 32 : DH) | (1u << 16);    // O: B (= V, or [V | ones]) is MN-major
       constexpr uint32_t idesc_l = umma_idesc_f16(BF, BM, 16);                 // row sums: B = a 16 x 16 tile of ones
       const int ring_id = SHARED ? 0 : slot;
       uint8_t* ring = sRing + ring_id * STAGES * G::STAGE_BYTES;
-      uint64_t* rfull = kv_full + ring_id * STAGES;
-      uint64_t* rempty = kv_empty + ring_id * STAGES;
-      const bool loader = SHARED ? slot == 0 : true;
-      // The slot's work is a FLAT stream of (item, chunk) steps.  Three cursors walk it in a fixed order - loads run up to
-      // STAGES chunks ahead (non-blocking probe of the ring), S is issued one chunk ahead of the softmax warps, PV follows
-      // the softmax warps - so that the next item's Q, its K/V chunks and its first S are already under way while the
-      // softmax warps finish the tail and the epilogue of the current item.  Every wait in the order below is for something
-      // the other side produces without needing this thread, hence the blocking (suspending) waits.
-      const int n_my = first < p.nitems ? (p.nitems - first + stride - 1) / stride : 0;
+      const uint32_t a_ring = smem_u32(ring), a_q = smem_u32(sQ + slot * 2 * G::Q_BYTES);
+      const uint32_t rfull = a_kv_full + 8 * ring_id * STAGES, rempty = a_kv_empty + 8 * ring_id * STAGES;
+      const uint32_t b_q_full = a_q_full + 16 * slot, b_q_empty = a_q_empty + 16 * slot;
+      const uint32_t b_s_full = a_s_full + 8 * slot, b_s_free = a_s_free + 8 * slot, b_p_full = a_p_full + 8 * slot, b_p_empty = a_p_empty + 8 * slot;
+      const uint32_t b_o_full = a_o_full + 8 * slot, b_o_free = a_o_free + 8 * slot;
+      const int first = first_of(slot);
+      const int n_my = count_of(slot);
       const uint32_t total = static_cast<uint32_t>(n_my) * nchunks;
-      struct Cur {                     // (item index, chunk) position of a cursor; a / b: what that cursor needs of the item
-        int i, j, a, b;
-        bool active;
+      auto active_at = [&](int i) -> bool {
+        if (!SHARED) return true;
+        if (i >= n_my) return false;
+        int seq, head, qt;
+        return decode(first + i * stride, slot, seq, head, qt);
       };
-      auto cur_set = [&](Cur& cu, int i, int kind) {               // kind 0: activity only, 1: loader (row0, head), 2: Q (row, head)
-        int seq = 0, head = 0, qtile = 0;
-        cu.i = i;
-        cu.j = 0;
-        cu.active = i < n_my ? decode(first + i * stride, seq, head, qtile) : false;
-        cu.a = kind == 1 ? seq * p.seqlen : seq * p.seqlen + qtile * BM;
-        cu.b = head * DH;
-      };
-      auto cur_next = [&](Cur& cu, int kind) {
-        if (++cu.j == nchunks) cur_set(cu, cu.i + 1, kind);
-      };
-      Cur L, Sx, Px, Qx;
-      cur_set(L, 0, 1);
-      cur_set(Sx, 0, 0);
-      cur_set(Px, 0, 0);
-      cur_set(Qx, 0, 2);
-      uint32_t lc = 0, sc = 0, pc = 0;
-      uint32_t aq = 0;                 // active items whose Q was requested
-      uint32_t n_s = 0, n_pv = 0;      // S / PV issued by this slot (active items only)
-      uint32_t as_item = 0;            // active items whose S phase is complete
-      uint32_t n_item = 0;             // active items completed (o_full committed)
-      auto load_next_q = [&]() {       // Q tile of the next active item into buffer aq & 1
-        while (Qx.i < n_my && !Qx.active) cur_set(Qx, Qx.i + 1, 2);
-        if (Qx.i >= n_my) return;
-        const uint32_t buf = aq & 1;
-        if (aq >= 2) SL_WAIT(&q_empty[slot * 2 + buf], ((aq >> 1) - 1) & 1);
-        mbar_arrive_expect_tx(&q_full[slot * 2 + buf], G::Q_BYTES);
-        tma_load_2d(sQ + (slot * 2 + buf) * G::Q_BYTES, &tmQ, &q_full[slot * 2 + buf], Qx.b, Qx.a);
-        ++aq;
-        cur_set(Qx, Qx.i + 1, 2);
-      };
-      auto top_up = [&]() {            // K/V chunks as far ahead as the ring allows (in lock-step mode slot 0 loads for everybody)
-        while (loader && lc < total) {
-          const int st = lc % STAGES;
-          if (lc >= static_cast<uint32_t>(STAGES) && !mbar_test(&rempty[st], ((lc / STAGES) - 1) & 1)) break;
-          const int row = L.a + L.j * BK;
-          mbar_arrive_expect_tx(&rfull[st], G::STAGE_BYTES);
-          tma_load_2d(ring + st * G::STAGE_BYTES, &tmKV, &rfull[st], p.C + L.b, row);
-          tma_load_2d(ring + st * G::STAGE_BYTES + G::KV_BYTES, &tmKV, &rfull[st], 2 * p.C + L.b, row);
-          ++lc;
-          cur_next(L, 1);
+      // descriptors of stage 0; a stage further on adds STAGE_BYTES to the start address (and, with the fused sums, takes the
+      // same amount off the leading byte offset that reaches the fixed block of ones)
+      constexpr uint64_t STAGE_D = G::STAGE_BYTES >> 4;
+      const uint64_t qd[2] = {desc(a_q, SBO, LAYOUT), desc(a_q + G::Q_BYTES, SBO, LAYOUT)};
+      const uint64_t kd0 = desc(a_ring, SBO, LAYOUT);
+      const uint32_t vaddr0 = a_ring + G::KV_BYTES;
+      uint64_t vd0[BK / 16];
+#pragma unroll
+      for (int kk = 0; kk < BK / 16; ++kk) {
+        const uint32_t va = vaddr0 + 16 * PITCH * kk;
+        vd0[kk] = FUSED ? desc_lbo(va, SBO, LAYOUT, smem_u32(sOnes) - va) : desc(va, SBO, LAYOUT);
+      }
+      constexpr uint64_t V_STEP = FUSED ? (STAGE_D - (STAGE_D << 16)) : STAGE_D;
+      const uint64_t odesc = desc(smem_u32(sOnes), 256, 6u);
+
+      // ---- loads.  K/V: fills f = l_f, l_f + LSTEP, ... of the ring (stage f mod STAGES, round f / STAGES)
+      constexpr int LSTEP = SHARED ? SLOTS : 1;
+      static_assert(LSTEP < STAGES, "one wrap per step");
+      uint32_t l_f = SHARED ? static_cast<uint32_t>(slot) : 0u, l_st = l_f, l_ph = 0;
+      int l_i = 0, l_j = static_cast<int>(l_f), l_row = 0, l_col = 0;
+      auto l_seek = [&]() {                                          // normalise (l_i, l_j) and look up the item's K/V rows
+        while (l_j >= nchunks) {
+          l_j -= nchunks;
+          ++l_i;
+        }
+        if (l_i < n_my) {
+          int seq, head, qt;
+          decode(first + l_i * stride, slot, seq, head, qt);
+          l_row = seq * p.seqlen;
+          l_col = head * DH;
         }
       };
+      l_seek();
+      auto top_up = [&]() {
+        while (l_i < n_my) {
+          if (l_f >= static_cast<uint32_t>(STAGES) && !test_a(rempty + 8 * l_st, l_ph ^ 1u)) break;
+          const uint32_t dst = a_ring + l_st * G::STAGE_BYTES;
+          const int row = l_row + l_j * BK;
+          expect_tx_a(rfull + 8 * l_st, G::STAGE_BYTES);
+          tma_2d_a(dst, &tmKV, rfull + 8 * l_st, p.C + l_col, row);
+          tma_2d_a(dst + G::KV_BYTES, &tmKV, rfull + 8 * l_st, 2 * p.C + l_col, row);
+          l_f += LSTEP;
+          l_st += LSTEP;
+          if (l_st >= static_cast<uint32_t>(STAGES)) {
+            l_st -= STAGES;
+            l_ph ^= 1u;
+          }
+          l_j += LSTEP;
+          if (l_j >= nchunks) l_seek();
+        }
+      };
+      // Q: two buffers, requested one item ahead
+      uint32_t aq = 0;                 // Q tiles requested
+      int q_i = 0;                     // next item whose Q tile is to be requested
+      auto load_next_q = [&]() {
+        int seq = 0, head = 0, qt = 0;
+        while (q_i < n_my && !decode(first + q_i * stride, slot, seq, head, qt)) ++q_i;
+        if (q_i >= n_my) return;
+        const uint32_t buf = aq & 1;
+        if (aq >= 2) SL_WAIT(b_q_empty + 8 * buf, ((aq >> 1) - 1) & 1);
+        expect_tx_a(b_q_full + 8 * buf, G::Q_BYTES);
+        tma_2d_a(a_q + buf * G::Q_BYTES, &tmQ, b_q_full + 8 * buf, head * DH, seq * p.seqlen + qt * BM);
+        ++aq;
+        ++q_i;
+      };
+
+      int sj = 0, si = 0, pj = 0, pi = 0;
+      bool s_act = active_at(0), p_act = s_act;
+      uint32_t s_st = 0, s_ph = 0, p_st = 0;
+      uint32_t sc = 0, pc = 0;
+      uint32_t n_s = 0, n_pv = 0;      // S / PV issued by this slot (active items only)
+      uint32_t as_item = 0;            // active items whose S phase has started / completed
+      uint32_t n_item = 0;             // active items completed (o_full committed)
       auto issue_s = [&]() {           // S(sc) = Q K^T
-        const int st = sc % STAGES;
-        SL_WAIT(&rfull[st], (sc / STAGES) & 1);
-        if (Sx.active) {
+        // The fill this S needs may be one this very thread still owes (its stage was not free at the last probe): keep
+        // probing the ring while waiting - a blocking wait here could wait for itself.
+        while (!try_wait_a(rfull + 8 * s_st, s_ph)) top_up();
+        if (s_act) {
           const uint32_t buf = as_item & 1;
-          if (Sx.j == 0) SL_WAIT(&q_full[slot * 2 + buf], (as_item >> 1) & 1);
-          if (n_s > 0) SL_WAIT(&s_free[slot], (n_s - 1) & 1);        // the softmax warps pulled the previous S out of TMEM
+          if (sj == 0) SL_WAIT(b_q_full + 8 * buf, (as_item >> 1) & 1);
+          if (n_s > 0) SL_WAIT(b_s_free, (n_s - 1) & 1);             // the softmax warps pulled the previous S out of TMEM
           tc_fence_after();
-          const uint64_t qdesc = desc(smem_u32(sQ + (slot * 2 + buf) * G::Q_BYTES), SBO, LAYOUT);
-          const uint64_t kdesc = desc(smem_u32(ring + st * G::STAGE_BYTES), SBO, LAYOUT);
+          const uint64_t kdesc = kd0 + STAGE_D * s_st;
 #pragma unroll
-          for (int kk = 0; kk < DH / 16; ++kk) umma_f16_ss(tslot + COL_S, qdesc + 2 * kk, kdesc + 2 * kk, idesc_s, kk != 0 ? 1u : 0u);
-          umma_commit(&s_full[slot]);
+          for (int kk = 0; kk < DH / 16; ++kk) umma_f16_ss(tslot + COL_S, qd[buf] + 2 * kk, kdesc + 2 * kk, idesc_s, kk != 0 ? 1u : 0u);
+          commit_a(b_s_full);
           ++n_s;
-          if (Sx.j + 1 == nchunks) {                                 // last S of the item: its Q buffer may be refilled once these MMAs are done
-            umma_commit(&q_empty[slot * 2 + buf]);
+          if (sj + 1 == nchunks) {                                   // last S of the item: its Q buffer may be refilled once these MMAs are done
+            commit_a(b_q_empty + 8 * buf);
             ++as_item;
           }
         }
         ++sc;
-        cur_next(Sx, 0);
+        if (++s_st == static_cast<uint32_t>(STAGES)) {
+          s_st = 0;
+          s_ph ^= 1u;
+        }
+        if (++sj == nchunks) {
+          sj = 0;
+          s_act = active_at(++si);
+        }
       };
       load_next_q();
       load_next_q();
@@ -387,58 +493,66 @@ __global__ void __launch_bounds__(THREADS, 1) attn_slots_kernel(const __grid_con
       while (pc < total) {
         top_up();
         if (sc < total) issue_s();                                   // S(pc + 1) runs while the softmax warps work on S(pc)
-        const int st = pc % STAGES;
-        if (Px.active) {
-          SL_WAIT(&p_full[slot], n_pv & 1);                          // P(pc) is in TMEM, O carries the current reference maximum
-          if (Px.j == 0 && n_item > 0) SL_WAIT(&o_free[slot], (n_item - 1) & 1);   // the previous item's O has been read out
+        if (p_act) {
+          SL_WAIT(b_p_full, n_pv & 1);                               // P(pc) is in TMEM, O carries the current reference maximum
+          if (pj == 0 && n_item > 0) SL_WAIT(b_o_free, (n_item - 1) & 1);   // the previous item's O has been read out
           tc_fence_after();
-          const uint64_t vdesc = desc(smem_u32(ring + st * G::STAGE_BYTES + G::KV_BYTES), SBO, LAYOUT);
-          const uint64_t odesc = desc(smem_u32(sOnes), 256, 6u);
+          const uint32_t acc0 = pj != 0 ? 1u : 0u;
 #pragma unroll
           for (int kk = 0; kk < BK / 16; ++kk) {                     // 16 keys per MMA: A advances 8 TMEM columns, B 16 rows
-            mma_ts(tslot + COL_O, tslot + COL_P + 8 * kk, vdesc + ((16 * PITCH) >> 4) * kk, idesc_o, (Px.j | kk) != 0 ? 1u : 0u);
-            if (SUMS) mma_ts(tslot + COL_L, tslot + COL_P + 8 * kk, odesc, idesc_l, (Px.j | kk) != 0 ? 1u : 0u);   // row sums of the rounded P
+            const uint32_t acc = kk != 0 ? 1u : acc0;
+            mma_ts(tslot + COL_O, tslot + COL_P + 8 * kk, vd0[kk] + V_STEP * p_st, idesc_o, acc);
+            if (SUMS && !FUSED) mma_ts(tslot + COL_L, tslot + COL_P + 8 * kk, odesc, idesc_l, acc);   // row sums of the rounded P
           }
-          umma_commit(&p_empty[slot]);
-          umma_commit(&rempty[st]);
+          commit_a(b_p_empty);
+          commit_a(rempty + 8 * p_st);
           ++n_pv;
-          if (Px.j + 1 == nchunks) {
-            umma_commit(&o_full[slot]);
+          if (pj + 1 == nchunks) {
+            commit_a(b_o_full);
             ++n_item;
             load_next_q();                                           // the Q buffer of the item before this one is free by now
           }
         } else {
-          mbar_arrive(&rempty[st]);                                  // an idle slot of a lock-step item still releases the stage
+          arrive_a(rempty + 8 * p_st);                               // an idle slot of a lock-step item still releases the stage
         }
         ++pc;
-        cur_next(Px, 0);
+        if (++p_st == static_cast<uint32_t>(STAGES)) p_st = 0;
+        if (++pj == nchunks) {
+          pj = 0;
+          p_act = active_at(++pi);
+        }
       }
     }
   } else {
     reg_inc<104>();
+    const int slot = warp >> 2;
+    const uint32_t tslot = tmem + static_cast<uint32_t>(slot) * G::SLOT_COLS;
+    const int first = first_of(slot);
     // ---------------------------------------------------------------------- softmax / epilogue: one thread per query row
     const int quarter = warp & 3;                                  // TMEM lane quarter this warp may access
     const int r = quarter * 32 + lane;
     const uint32_t tbase = tslot + (static_cast<uint32_t>(quarter * 32) << 16);
     const float c = p.scale_log2;
     const uint64_t c2 = pk2(c, c);
+    const uint32_t b_s_full = a_s_full + 8 * slot, b_s_free = a_s_free + 8 * slot, b_p_full = a_p_full + 8 * slot, b_p_empty = a_p_empty + 8 * slot;
+    const uint32_t b_o_full = a_o_full + 8 * slot, b_o_free = a_o_free + 8 * slot;
+    const bool elected = lane == 0;
     uint32_t n_c = 0, n_item = 0;
     for (int item = first; item < p.nitems; item += stride) {
       int seq, head, qtile;
-      if (!decode(item, seq, head, qtile)) continue;
+      if (!decode(item, slot, seq, head, qtile)) continue;
       float m_ref = -INFINITY;
       uint64_t lsum2 = pk2(0.f, 0.f);
       for (int j = 0; j < nchunks; ++j, ++n_c) {
         float v[64];
-        SL_WAIT(&s_full[slot], n_c & 1);
+        SL_WAIT(b_s_full, n_c & 1);
         tc_fence_after();
-        __syncwarp();
         ld_x32(tbase + COL_S, v);
         ld_x32(tbase + COL_S + 32, v + 32);
         tmem_ld_wait();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&s_free[slot]);                 // one elected arrival per warp
+        if (elected) arrive_a(b_s_free);                           // one elected arrival per warp
         const int nvalid = min(BK, p.seqlen - j * BK);             // keys >= nvalid belong to the next sequence / are padding
         // ---- row maximum of the valid keys.  Ragged chunks are handled in groups of 8 keys with warp-uniform branches:
         // full groups take the unmasked code, only the group that holds the boundary pays for per-key predicates.
@@ -512,7 +626,7 @@ __global__ void __launch_bounds__(THREADS, 1) attn_slots_kernel(const __grid_con
           }
         }
         // only now wait for PV(j-1): its latency hides behind the exponentials above (P is single-buffered)
-        if (n_c > 0) SL_WAIT(&p_empty[slot], (n_c - 1) & 1);
+        if (n_c > 0) SL_WAIT(b_p_empty, (n_c - 1) & 1);
         tc_fence_after();
         if (j > 0 && __any_sync(0xffffffffu, move)) {               // rare after the first chunks: rescale this row of O (and of l)
 #pragma unroll
@@ -527,16 +641,15 @@ __global__ void __launch_bounds__(THREADS, 1) attn_slots_kernel(const __grid_con
             st_x16(tbase + COL_O + cc * 16, u16);
           }
         }
-        __syncwarp();
         st_x16(tbase + COL_P, pk);
         st_x16(tbase + COL_P + 16, pk + 16);
         st_wait();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&p_full[slot]);
+        if (elected) arrive_a(b_p_full);
       }
       // ---- O / l -> global
-      SL_WAIT(&o_full[slot], n_item & 1);
+      SL_WAIT(b_o_full, n_item & 1);
       tc_fence_after();
       float inv;
       if (SUMS) {
@@ -564,7 +677,7 @@ __global__ void __launch_bounds__(THREADS, 1) attn_slots_kernel(const __grid_con
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&o_free[slot]);
+      if (elected) arrive_a(b_o_free);
       ++n_item;
       if (qrow < p.seqlen) {
 #pragma unroll
@@ -574,7 +687,7 @@ __global__ void __launch_bounds__(THREADS, 1) attn_slots_kernel(const __grid_con
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) {
+  if (warp == W_DRIVER) {
     tc_fence_after();
     tmem_dealloc(tmem, 512);
   }
@@ -596,7 +709,7 @@ static WaitDbg* debug_buffer() {
   return dev;
 }
 
-template <typename T, int DH, bool SHARED, uint32_t PMASK>
+template <typename T, int DH, bool SHARED, uint32_t PMASK, bool FUSED>
 static int launch_m(const AttnArgs& a, int C, cudaStream_t st) {
   using G = Geo<DH, SHARED>;
   CUtensorMap tq, tkv;
@@ -619,22 +732,54 @@ static int launch_m(const AttnArgs& a, int C, cudaStream_t st) {
   // One CTA per SM (it allocates all 512 TMEM columns): more than half of the shared memory is requested so that a second
   // CTA can never become resident and spin inside tcgen05.alloc.
   const size_t smem = std::max<size_t>(G::SMEM, 116 * 1024);
-  if (int e = ensure_max_dyn_smem(reinterpret_cast<const void*>(attn_slots_kernel<T, DH, SHARED, PMASK>), 227 * 1024)) return e;
+  if (int e = ensure_max_dyn_smem(reinterpret_cast<const void*>(attn_slots_kernel<T, DH, SHARED, PMASK, FUSED>), 227 * 1024)) return e;
   const long long ctas = SHARED ? nitems : (nitems + SLOTS - 1) / SLOTS;
   const unsigned grid = static_cast<unsigned>(std::min<long long>(ctas, current_device_sms()));
-  launch_k(attn_slots_kernel<T, DH, SHARED, PMASK>, dim3(grid), dim3(THREADS), smem, st, tq, tkv, p);
+  launch_k(attn_slots_kernel<T, DH, SHARED, PMASK, FUSED>, dim3(grid), dim3(THREADS), smem, st, tq, tkv, p);
   return static_cast<int>(cudaGetLastError());
 }
 
-// Which pairs (index mod 8) take the polynomial exp2: 3 of 8 (see the header); LWB_SLOTS_PMASK overrides for A/B runs.
-#ifndef LWB_SLOTS_PMASK
-#define LWB_SLOTS_PMASK 0x49u
-#endif
+// Which pairs (index mod 8) take the polynomial exp2.  The register-only microbenchmark is fastest at 3 of 8; the kernel, whose
+// softmax threads also pull S, store P and synchronise, is issue-bound earlier: measured 309 / 311 / 326 / 336 us with
+// 0 / 1 / 2 / 3 of 8 pairs on the polynomial (small / B = 32 global attention), 111 / 113 / 113 / 125 us for the medium
+// windows - so the default is 0 (all exponentials on the MUFU); LWDETR_B200_SLOTS_POLY = 0..3 selects for A/B runs.
+static int slots_poly() {
+  static int v = [] {
+    const char* e = getenv("LWDETR_B200_SLOTS_POLY");
+    return e ? atoi(e) : 0;
+  }();
+  return v;
+}
+
+// LWDETR_B200_SLOTS_MODE (A/B measurements): bit 0 = independent slots (own K/V ring each) for long sequences too,
+// bit 1 = fused row sums (head dim 16).  Default 3, measured on small / B = 32 global attention (profiles/r02j): lock-step +
+// separate sums 391 us, independent 360, lock-step + fused 358, independent + fused 336 (all with 3/8 polynomial exps).
+static int slots_mode() {
+  static int v = [] {
+    const char* e = getenv("LWDETR_B200_SLOTS_MODE");
+    return e ? atoi(e) : 3;
+  }();
+  return v;
+}
+
+template <typename T, int DH, uint32_t PMASK>
+static int launch_p(const AttnArgs& a, int C, cudaStream_t st) {
+  const int mode = slots_mode();
+  const bool indep = a.seqlen <= BM || (mode & 1);
+  if constexpr (DH == 16) {
+    if (mode & 2) return indep ? launch_m<T, DH, false, PMASK, true>(a, C, st) : launch_m<T, DH, true, PMASK, true>(a, C, st);
+  }
+  return indep ? launch_m<T, DH, false, PMASK, false>(a, C, st) : launch_m<T, DH, true, PMASK, false>(a, C, st);
+}
 
 template <typename T, int DH>
 static int launch(const AttnArgs& a, int C, cudaStream_t st) {
-  if (a.seqlen <= BM) return launch_m<T, DH, false, LWB_SLOTS_PMASK>(a, C, st);
-  return launch_m<T, DH, true, LWB_SLOTS_PMASK>(a, C, st);
+  switch (slots_poly()) {
+    case 0: return launch_p<T, DH, 0x00u>(a, C, st);
+    case 1: return launch_p<T, DH, 0x01u>(a, C, st);
+    case 2: return launch_p<T, DH, 0x11u>(a, C, st);
+    default: return launch_p<T, DH, 0x49u>(a, C, st);
+  }
 }
 
 }  // namespace sl

@@ -7,11 +7,11 @@
 // 1. msda_fwd_kernel - the model path.  The reference gathers 32-byte head slices from a token-major value tensor:
 //    every bilinear corner is a random DRAM sector.  Here value_proj writes the value tensor HEAD-MAJOR
 //    ([image][head][token][16], gemm_tc "head-major" epilogue), so everything one (image, head) can ever sample is
-//    ONE contiguous slab (51 KB at 40x40).  Persistent CTAs (one per SM, two independent halves of 10 warps) walk the
-//    (image, head) items: the slab is streamed - in bands of <= 1680 tokens - into a two-stage shared-memory ring per
-//    half with 1-D bulk copies (cp.async.bulk + mbarrier complete_tx; measured 7.0 TB/s at this chunk size,
-//    profiles/r02c_ubench_stream.txt), the threads (one = all 16 channels of one query) take the bilinear corners out
-//    of shared memory.  DRAM sees the value tensor exactly once, as a linear stream; the softmax over
+//    ONE contiguous slab (51 KB at 40x40).  Persistent CTAs (one per SM, 20 warps) walk the (image, head) items: the
+//    slab is streamed - in bands of <= 1680 tokens - into a four-stage shared-memory ring with 1-D bulk copies
+//    (cp.async.bulk + mbarrier complete_tx; measured 7.0 TB/s at this chunk size, profiles/r02c_ubench_stream.txt),
+//    the threads (two per (query, head): half of the samples each, all 16 channels) take the bilinear corners out of
+//    shared memory.  DRAM sees the value tensor exactly once, as a linear stream; the softmax over
 //    the L*P logits, the sampling-location arithmetic (incl. valid ratios of padded batches) and the weighted sum
 //    stay in registers; the raw projections of the NEXT item are prefetched while the current one is sampled.
 //    A P3 level (80x80 = 205 KB per head) does not fit a stage: it is cut into bands of 21 rows (one halo row), each
@@ -28,12 +28,13 @@
 
 namespace lwb {
 
-static constexpr int MS_STAGES = 4;                                // two per consumer group
+static constexpr int MS_STAGES = 4;                                // slabs / bands in flight per CTA
 static constexpr int MS_STAGE_TOKENS = 1680;                       // 21 rows of 80 / 42 rows of 40
 static constexpr int MS_STAGE_BYTES = MS_STAGE_TOKENS * MSDA_D * 2;
-static constexpr int MS_GROUP_WARPS = 10;                          // 320 threads = 320 queries per pass
-static constexpr int MS_QPASS = MS_GROUP_WARPS * 32;
-static constexpr int MS_THREADS = 2 * MS_QPASS;                    // 20 warps => 96 registers / thread
+static constexpr int MS_TPQ = 2;                                   // threads per (query, head): each takes half of the L*P samples
+static constexpr int MS_WARPS = 20;
+static constexpr int MS_THREADS = MS_WARPS * 32;                   // 640 threads = 320 queries per pass
+static constexpr int MS_QPASS = MS_THREADS / MS_TPQ;
 static constexpr int MS_SMEM = MS_STAGES * MS_STAGE_BYTES + 128;
 
 __device__ __forceinline__ U4 lds16(uint32_t addr) {
@@ -41,27 +42,52 @@ __device__ __forceinline__ U4 lds16(uint32_t addr) {
   asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr));
   return r;
 }
+// one 32-bit word = two 16-bit values -> packed fp32 pair (low element first), on the ALU pipe (the FMA pipe is the busy one)
+template <typename T> __device__ __forceinline__ uint64_t widen2(uint32_t w);
+template <> __device__ __forceinline__ uint64_t widen2<__nv_bfloat16>(uint32_t w) {
+  uint64_t r;
+  asm("{\n\t.reg .b32 lo, hi;\n\tshl.b32 lo, %1, 16;\n\tand.b32 hi, %1, 0xffff0000;\n\tmov.b64 %0, {lo, hi};\n\t}" : "=l"(r) : "r"(w));
+  return r;
+}
+template <> __device__ __forceinline__ uint64_t widen2<__half>(uint32_t w) {
+  uint64_t r;
+  asm("{\n\t.reg .b16 l, h;\n\t.reg .f32 fl, fh;\n\tmov.b32 {l, h}, %1;\n\tcvt.f32.f16 fl, l;\n\tcvt.f32.f16 fh, h;\n\tmov.b64 %0, {fl, fh};\n\t}"
+      : "=l"(r) : "r"(w));
+  return r;
+}
+__device__ __forceinline__ uint64_t shfl_xor1_b64(uint64_t v) {
+  uint32_t lo = static_cast<uint32_t>(v), hi = static_cast<uint32_t>(v >> 32);
+  lo = __shfl_xor_sync(0xffffffffu, lo, 1);
+  hi = __shfl_xor_sync(0xffffffffu, hi, 1);
+  return (static_cast<uint64_t>(hi) << 32) | lo;
+}
 
-// ncu of the first version of this kernel (profiles/r02d_ncu_msda_small.txt) showed it bound by its own instruction
-// stream, not by memory: 550 instructions per (query, head, 8-channel half) - half of them index / predicate arithmetic
-// that both halves repeated, plus one conversion and one FFMA per value.  Hence: ONE thread owns all 16 channels of a
-// (query, head) (the scalar work is done once), the accumulation runs on packed fp32x2 FMAs, addresses are 32-bit
-// shared-memory offsets.  The CTA is two independent halves of 10 warps, each walking its own (image, head) items with
-// its own two-stage ring; lane 0 of each half's first warp is its producer (it re-arms a stage as soon as its half has
-// released it), so a slab is loading for each half while the other slab is being sampled.
+// ncu of the earlier versions of this kernel (profiles/r02d_ncu_msda_small.txt, r02g_ncu_msda_medium.txt) showed it bound by
+// its own instruction stream and by a tail, not by memory: 735 instructions per (query, head) - a fifth of them integer
+// divisions of the item / pass bookkeeping, another third register shuffling around the 16-bit -> fp32 unpack - at 36 % issue
+// utilisation, with half-CTAs that each walked whole (image, head) items (3.46 items per half at medium / B = 64: 14 % tail).
+// Hence:
+//   * the whole CTA (20 warps) works on ONE (image, head) slab at a time; slabs stream through a 4-stage ring filled by one
+//     elected thread (cp.async.bulk + mbarrier complete_tx), so up to three slabs are in flight behind the one being sampled;
+//   * TWO threads per (query, head): each takes half of the L*P samples (all 16 channels), the pair exchanges halves of its
+//     partial sums with 8 shuffles and each stores 8 channels - 600 of 640 threads busy at nq = 300;
+//   * item / image / head counters are incremental (no division in any loop), the unpack is two ALU operations per pair,
+//     the accumulation runs on packed fp32x2 FMAs.
 template <typename T, int NL, int NP>   // levels, points per head and level
 __global__ void __launch_bounds__(MS_THREADS, 1) msda_fwd_kernel(const __grid_constant__ MsdaArgs p) {
   constexpr int LP = NL * NP;
+  constexpr int SPT = LP / MS_TPQ;                             // samples per thread: i = sub + 2*k (levels stay balanced)
+  static_assert(LP % MS_TPQ == 0 && NP % MS_TPQ == 0, "samples split evenly between the two threads of a query");
   extern __shared__ __align__(128) uint8_t ms_smem[];
   uint64_t* full = reinterpret_cast<uint64_t*>(ms_smem + MS_STAGES * MS_STAGE_BYTES);
   uint64_t* empty = full + MS_STAGES;
-  const int grp = threadIdx.x / MS_QPASS;                     // consumer half 0 / 1
-  const int gt = threadIdx.x - grp * MS_QPASS;                // thread in the half = query index in a pass
   const int lane = threadIdx.x & 31;
+  const int sub = threadIdx.x & 1;                              // which half of the samples / which 8 channels are stored
+  const int qt = threadIdx.x >> 1;                              // query index inside a pass
   if (threadIdx.x == 0) {
     for (int s = 0; s < MS_STAGES; ++s) {
       mbar_init(&full[s], 1);
-      mbar_init(&empty[s], MS_GROUP_WARPS);
+      mbar_init(&empty[s], MS_WARPS);
     }
     fence_mbar_init();
   }
@@ -69,160 +95,187 @@ __global__ void __launch_bounds__(MS_THREADS, 1) msda_fwd_kernel(const __grid_co
   pdl_sync();   // programmatic dependent launch: release the successor, wait for the predecessor (launch.h)
   const int nitems = p.batch * p.heads;
   const int npass = (p.nq + MS_QPASS - 1) / MS_QPASS;
-  const int first = static_cast<int>(blockIdx.x) * 2 + grp, stride = static_cast<int>(gridDim.x) * 2;
+  const int first = static_cast<int>(blockIdx.x), stride = static_cast<int>(gridDim.x);
   const int n_my = first < nitems ? (nitems - first + stride - 1) / stride : 0;
-  const int steps_per_item = npass * p.nbands;
-  const int total = n_my * steps_per_item;                    // (item, pass, band) steps of this half
-  uint64_t* gfull = full + 2 * grp;
-  uint64_t* gempty = empty + 2 * grp;
-  const uint32_t gstage = smem_u32(ms_smem) + static_cast<uint32_t>(2 * grp) * MS_STAGE_BYTES;
-  const bool producer = gt == 0;
-  auto issue_load = [&](int t) {                              // step t of this half -> stage t & 1
-    const int item = first + (t / steps_per_item) * stride, k = t % p.nbands;
-    const int b = item / p.heads, m = item - b * p.heads;
-    const T* slab = reinterpret_cast<const T*>(p.value) + static_cast<long long>(b) * p.v_b_stride + static_cast<long long>(m) * p.S * MSDA_D;
-    mbar_arrive_expect_tx(&gfull[t & 1], static_cast<uint32_t>(p.bands[k].bytes));
-    bulk_load(ms_smem + (2 * grp + (t & 1)) * MS_STAGE_BYTES, slab + static_cast<long long>(p.bands[k].tok0) * MSDA_D, static_cast<uint32_t>(p.bands[k].bytes),
-              &gfull[t & 1]);
+  const int db = stride / p.heads, dm = stride - db * p.heads;  // item += stride  <=>  (b, m) += (db, dm) with carry
+  const int total = n_my * npass * p.nbands;                    // (item, pass, band) steps of this CTA
+  const uint32_t smem0 = smem_u32(ms_smem);
+
+  // ---- producer state (thread 0): next step to load
+  int ld_t = 0, ld_k = 0, ld_pass = 0, ld_b = first / p.heads, ld_m = first - (first / p.heads) * p.heads;
+  uint32_t ld_st = 0, ld_ph = 0;
+  auto issue_load = [&]() {                                    // step ld_t -> stage ld_st
+    if (ld_t >= MS_STAGES) mbar_wait(&empty[ld_st], ld_ph ^ 1u);
+    const T* slab = reinterpret_cast<const T*>(p.value) + static_cast<long long>(ld_b) * p.v_b_stride + static_cast<long long>(ld_m) * p.S * MSDA_D;
+    const uint32_t bytes = static_cast<uint32_t>(p.bands[ld_k].bytes);
+    mbar_arrive_expect_tx(&full[ld_st], bytes);
+    bulk_load(ms_smem + ld_st * MS_STAGE_BYTES, slab + static_cast<long long>(p.bands[ld_k].tok0) * MSDA_D, bytes, &full[ld_st]);
+    ++ld_t;
+    if (++ld_st == MS_STAGES) {
+      ld_st = 0;
+      ld_ph ^= 1u;
+    }
+    if (++ld_k == p.nbands) {
+      ld_k = 0;
+      if (++ld_pass == npass) {
+        ld_pass = 0;
+        ld_m += dm;
+        ld_b += db;
+        if (ld_m >= p.heads) {
+          ld_m -= p.heads;
+          ++ld_b;
+        }
+      }
+    }
   };
+  const bool producer = threadIdx.x == 0;
   if (producer) {
-    if (total > 0) issue_load(0);
-    if (total > 1) issue_load(1);
+    for (int i = 0; i < MS_STAGES - 1 && ld_t < total; ++i) issue_load();
   }
+
   struct Raw {
-    uint32_t off[LP];          // (dx, dy) 16-bit pairs
-    uint32_t lg[LP / 2];       // logits, 16-bit pairs
+    uint32_t off[SPT];         // (dx, dy) 16-bit pairs of this thread's samples
+    uint32_t lg[LP / 2];       // all logits of the (query, head), 16-bit pairs
     float4 ref;
   };
-  auto load_raw = [&](int ip, Raw& r) {                       // ip = (item, pass) index of this half
-    if (ip >= n_my * npass) return;
-    const int item = first + (ip / npass) * stride, q = (ip % npass) * MS_QPASS + gt;
+  auto load_raw = [&](int b, int m, int q, Raw& r) {
     if (q >= p.nq) return;
-    const int b = item / p.heads, m = item - b * p.heads;
     const long long row = static_cast<long long>(b) * p.nq + q;
     const T* oa = reinterpret_cast<const T*>(p.offs_logits) + row * p.ld_ol;
     const uint32_t* o32 = reinterpret_cast<const uint32_t*>(oa + m * (2 * LP));
 #pragma unroll
-    for (int i = 0; i < LP; ++i) r.off[i] = __ldg(o32 + i);
+    for (int k = 0; k < SPT; ++k) r.off[k] = __ldg(o32 + sub + MS_TPQ * k);
     const uint32_t* l32 = reinterpret_cast<const uint32_t*>(oa + p.heads * (2 * LP) + m * LP);
 #pragma unroll
     for (int i = 0; i < LP / 2; ++i) r.lg[i] = __ldg(l32 + i);
     r.ref = __ldg(reinterpret_cast<const float4*>(p.ref) + row);
   };
-  // the raw projections of the NEXT (item, pass) are prefetched while the current one is sampled - where the registers
-  // allow it (L*P <= 4: 7 registers); with 8 samples per head they are loaded on demand (once per five bands)
-  constexpr bool PREFETCH = LP <= 4;
+
+  int b = first / p.heads, m = first - b * p.heads;
+  // the raw projections of the NEXT (item, pass) are prefetched while the current one is sampled
   Raw nxt;
-  if (PREFETCH) load_raw(0, nxt);
+  if (n_my > 0) load_raw(b, m, qt, nxt);
+  uint32_t c_st = 0, c_ph = 0;                                  // consumer stage / phase
   int t = 0;
-  for (int ip = 0; ip < n_my * npass; ++ip) {
-    const int item = first + (ip / npass) * stride, q = (ip % npass) * MS_QPASS + gt;
-    const int b = item / p.heads, m = item - b * p.heads;
-    const bool active = q < p.nq;
-    Raw cur;
-    if (PREFETCH) {
-      cur = nxt;
-      load_raw(ip + 1, nxt);
-    } else {
-      load_raw(ip, cur);
+  for (int it = 0; it < n_my; ++it) {
+    int nb = b + db, nm = m + dm;
+    if (nm >= p.heads) {
+      nm -= p.heads;
+      ++nb;
     }
-    // ---- per-(query, head) sample table: image coordinates and softmax weight (0 when the sample is outside)
-    float px[LP], py[LP], pw[LP];
-    if (active) {
-      float mx = -INFINITY;
-#pragma unroll
-      for (int i = 0; i < LP / 2; ++i) {
-        const float2 f = Cvt<T>::unpack(cur.lg[i]);
-        pw[2 * i] = f.x;
-        pw[2 * i + 1] = f.y;
-        mx = fmaxf(mx, fmaxf(f.x, f.y));
-      }
-      float sum = 0.f;
-#pragma unroll
-      for (int i = 0; i < LP; ++i) {
-        pw[i] = __expf(pw[i] - mx);
-        sum += pw[i];
-      }
-      const float inv = __fdividef(1.f, sum);
-      const float sx = cur.ref.z * (0.5f / NP), sy = cur.ref.w * (0.5f / NP);
-#pragma unroll
-      for (int i = 0; i < LP; ++i) {
-        const int l = i / NP;
-        const float2 o = Cvt<T>::unpack(cur.off[i]);
-        float lx = cur.ref.x + o.x * sx, ly = cur.ref.y + o.y * sy;      // ms_deform_attn.py:125-127
-        if (p.valid_ratio != nullptr) {                                  // transformer.py:352-353: boxes scaled per level
-          lx *= __ldg(p.valid_ratio + (b * NL + l) * 2);
-          ly *= __ldg(p.valid_ratio + (b * NL + l) * 2 + 1);
-        }
-        const float H = static_cast<float>(p.lvl_h[l]), W = static_cast<float>(p.lvl_w[l]);
-        px[i] = lx * W - 0.5f;                                           // cuh:285-286
-        py[i] = ly * H - 0.5f;
-        const bool in = py[i] > -1.f && px[i] > -1.f && py[i] < H && px[i] < W;   // cuh:288
-        pw[i] = in ? pw[i] * inv : 0.f;
-      }
-    }
-    uint64_t acc[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) acc[i] = f2_pack(0.f, 0.f);
-    for (int k = 0; k < p.nbands; ++k, ++t) {
-      const int own0 = p.bands[k].own0, own1 = p.bands[k].own1, row0 = p.bands[k].row0, blvl = p.bands[k].level;
-      mbar_wait(&gfull[t & 1], (t >> 1) & 1);
+    for (int pass = 0; pass < npass; ++pass) {
+      const int q = pass * MS_QPASS + qt;
+      const bool active = q < p.nq;
+      Raw cur = nxt;
+      if (pass + 1 < npass) load_raw(b, m, q + MS_QPASS, nxt);
+      else if (it + 1 < n_my) load_raw(nb, nm, qt, nxt);
+      // ---- this thread's samples: image coordinates and softmax weight (0 when the sample is outside)
+      float px[SPT], py[SPT], pw[SPT];
       if (active) {
-        const uint32_t stage = gstage + static_cast<uint32_t>(t & 1) * MS_STAGE_BYTES;
+        float lg[LP];
+        float mx = -INFINITY;
+#pragma unroll
+        for (int i = 0; i < LP / 2; ++i) {
+          const float2 f = Cvt<T>::unpack(cur.lg[i]);
+          lg[2 * i] = f.x;
+          lg[2 * i + 1] = f.y;
+          mx = fmaxf(mx, fmaxf(f.x, f.y));
+        }
+        float sum = 0.f;
 #pragma unroll
         for (int i = 0; i < LP; ++i) {
-          if (NL > 1 && i / NP != blvl) continue;                        // uniform
-          const int H = p.lvl_h[i / NP], W = p.lvl_w[i / NP];
-          const float yf = floorf(py[i]), xf = floorf(px[i]);
-          const int y0 = static_cast<int>(yf), x0 = static_cast<int>(xf);
-          if (pw[i] == 0.f || y0 < own0 || y0 > own1) continue;
-          const float ly = py[i] - yf, lx = px[i] - xf;
-          // all four corner reads are issued unconditionally (clamped address, zero weight outside the image)
-          const int ya = max(y0, 0), yb = min(y0 + 1, H - 1), xa = max(x0, 0), xb = min(x0 + 1, W - 1);
-          const float wy0 = y0 >= 0 ? pw[i] - pw[i] * ly : 0.f, wy1 = y0 + 1 < H ? pw[i] * ly : 0.f;
-          const float wx0 = x0 >= 0 ? 1.f - lx : 0.f, wx1 = x0 + 1 < W ? lx : 0.f;
-          const uint32_t ra = stage + static_cast<uint32_t>((ya - row0) * W) * 32u, rb = stage + static_cast<uint32_t>((yb - row0) * W) * 32u;
-          const uint32_t a00 = ra + xa * 32, a01 = ra + xb * 32, a10 = rb + xa * 32, a11 = rb + xb * 32;
-          const uint32_t addr[4] = {a00, a01, a10, a11};
-          const float wc[4] = {wy0 * wx0, wy0 * wx1, wy1 * wx0, wy1 * wx1};
+          lg[i] = __expf(lg[i] - mx);
+          sum += lg[i];
+        }
+        const float inv = __fdividef(1.f, sum);
+        const float sx = cur.ref.z * (0.5f / NP), sy = cur.ref.w * (0.5f / NP);
 #pragma unroll
-          for (int rowp = 0; rowp < 2; ++rowp) {                         // the two corners of one image row at a time (16 registers in flight)
-            const U4 v[4] = {lds16(addr[rowp * 2]), lds16(addr[rowp * 2] + 16), lds16(addr[rowp * 2 + 1]), lds16(addr[rowp * 2 + 1] + 16)};
+        for (int k = 0; k < SPT; ++k) {
+          const int l = k / (NP / MS_TPQ);                                 // sample i = sub + 2k lies in level i / NP = k / (NP / 2)
+          const float2 o = Cvt<T>::unpack(cur.off[k]);
+          float lx = cur.ref.x + o.x * sx, ly = cur.ref.y + o.y * sy;      // ms_deform_attn.py:125-127
+          if (p.valid_ratio != nullptr) {                                  // transformer.py:352-353: boxes scaled per level
+            lx *= __ldg(p.valid_ratio + (b * NL + l) * 2);
+            ly *= __ldg(p.valid_ratio + (b * NL + l) * 2 + 1);
+          }
+          const float H = static_cast<float>(p.lvl_h[l]), W = static_cast<float>(p.lvl_w[l]);
+          px[k] = lx * W - 0.5f;                                           // cuh:285-286
+          py[k] = ly * H - 0.5f;
+          const bool in = py[k] > -1.f && px[k] > -1.f && py[k] < H && px[k] < W;   // cuh:288
+          const float w = sub ? lg[2 * k + 1] : lg[2 * k];
+          pw[k] = in ? w * inv : 0.f;
+        }
+      }
+      uint64_t acc[8];
 #pragma unroll
-            for (int cx = 0; cx < 2; ++cx) {
-              const uint64_t w2 = f2_pack(wc[rowp * 2 + cx], wc[rowp * 2 + cx]);
+      for (int i = 0; i < 8; ++i) acc[i] = f2_pack(0.f, 0.f);
+      for (int k = 0; k < p.nbands; ++k, ++t) {
+        const int own0 = p.bands[k].own0, own1 = p.bands[k].own1, row0 = p.bands[k].row0, blvl = p.bands[k].level;
+        if (producer && t + MS_STAGES - 1 < total) issue_load();           // keep three loads in flight behind this one
+        mbar_wait(&full[c_st], c_ph);
+        if (active) {
+          const uint32_t stage = smem0 + c_st * MS_STAGE_BYTES;
 #pragma unroll
-              for (int hh = 0; hh < 2; ++hh) {
-                const U4 u = v[cx * 2 + hh];
-                const uint32_t uu[4] = {u.x, u.y, u.z, u.w};
+          for (int ks = 0; ks < SPT; ++ks) {
+            const int l = ks / (NP / MS_TPQ);
+            if (NL > 1 && l != blvl) continue;                             // uniform
+            const int H = p.lvl_h[l], W = p.lvl_w[l];
+            const float yf = floorf(py[ks]), xf = floorf(px[ks]);
+            const int y0 = static_cast<int>(yf), x0 = static_cast<int>(xf);
+            if (pw[ks] == 0.f || y0 < own0 || y0 > own1) continue;
+            const float ly = py[ks] - yf, lx = px[ks] - xf;
+            // all four corner reads are issued unconditionally (clamped address, zero weight outside the image)
+            const int ya = max(y0, 0), yb = min(y0 + 1, H - 1), xa = max(x0, 0), xb = min(x0 + 1, W - 1);
+            const float wy0 = y0 >= 0 ? pw[ks] - pw[ks] * ly : 0.f, wy1 = y0 + 1 < H ? pw[ks] * ly : 0.f;
+            const float wx0 = x0 >= 0 ? 1.f - lx : 0.f, wx1 = x0 + 1 < W ? lx : 0.f;
+            const uint32_t ra = stage + static_cast<uint32_t>((ya - row0) * W) * 32u, rb = stage + static_cast<uint32_t>((yb - row0) * W) * 32u;
+            const uint32_t addr[4] = {ra + xa * 32, ra + xb * 32, rb + xa * 32, rb + xb * 32};
+            const float wc[4] = {wy0 * wx0, wy0 * wx1, wy1 * wx0, wy1 * wx1};
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                  const float2 f = Cvt<T>::unpack(uu[j]);
-                  acc[hh * 4 + j] = f2_fma(w2, f2_pack(f.x, f.y), acc[hh * 4 + j]);
+            for (int rowp = 0; rowp < 2; ++rowp) {                         // the two corners of one image row at a time (16 registers in flight)
+              const U4 v[4] = {lds16(addr[rowp * 2]), lds16(addr[rowp * 2] + 16), lds16(addr[rowp * 2 + 1]), lds16(addr[rowp * 2 + 1] + 16)};
+#pragma unroll
+              for (int cx = 0; cx < 2; ++cx) {
+                const uint64_t w2 = f2_pack(wc[rowp * 2 + cx], wc[rowp * 2 + cx]);
+#pragma unroll
+                for (int hh = 0; hh < 2; ++hh) {
+                  const U4 u = v[cx * 2 + hh];
+                  const uint32_t uu[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) acc[hh * 4 + j] = f2_fma(w2, widen2<T>(uu[j]), acc[hh * 4 + j]);
                 }
               }
             }
           }
         }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[c_st]);
+        if (++c_st == MS_STAGES) {
+          c_st = 0;
+          c_ph ^= 1u;
+        }
       }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&gempty[t & 1]);
-      if (producer && t + 2 < total) {                                   // re-arm this stage as soon as the whole half has left it
-        mbar_wait(&gempty[t & 1], (t >> 1) & 1);
-        issue_load(t + 2);
-      }
-    }
-    if (active) {
-      U8 o;
+      // ---- the pair exchanges halves: sub 0 ends up with channels 0-7, sub 1 with channels 8-15 (all lanes take part)
+      uint64_t mine[4];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        float a0, a1;
-        f2_unpack(acc[j], a0, a1);
-        o.v[j] = Cvt<T>::pack(a0, a1);
+      for (int j = 0; j < 4; ++j) {
+        const uint64_t give = sub ? acc[j] : acc[4 + j];                   // what the partner stores
+        const uint64_t got = shfl_xor1_b64(give);
+        mine[j] = f2_add(sub ? acc[4 + j] : acc[j], got);
       }
-      const long long row = static_cast<long long>(b) * p.nq + q;
-      stg256(reinterpret_cast<T*>(p.out) + row * p.ld_out + m * MSDA_D, o);
+      if (active) {
+        U4 o;
+        float a0, a1;
+        f2_unpack(mine[0], a0, a1); o.x = Cvt<T>::pack(a0, a1);
+        f2_unpack(mine[1], a0, a1); o.y = Cvt<T>::pack(a0, a1);
+        f2_unpack(mine[2], a0, a1); o.z = Cvt<T>::pack(a0, a1);
+        f2_unpack(mine[3], a0, a1); o.w = Cvt<T>::pack(a0, a1);
+        const long long row = static_cast<long long>(b) * p.nq + q;
+        *reinterpret_cast<U4*>(reinterpret_cast<T*>(p.out) + row * p.ld_out + m * MSDA_D + sub * 8) = o;
+      }
     }
+    b = nb;
+    m = nm;
   }
 }
 
@@ -253,7 +306,7 @@ static int launch_fwd(const MsdaArgs& a, cudaStream_t st) {
   int e = ensure_max_dyn_smem(reinterpret_cast<const void*>(msda_fwd_kernel<T, NL, NP>), MS_SMEM);
   if (e) return e;
   const int items = a.batch * a.heads;
-  const unsigned grid = static_cast<unsigned>(std::min((items + 1) / 2, current_device_sms()));
+  const unsigned grid = static_cast<unsigned>(std::min(items, current_device_sms()));
   launch_k(msda_fwd_kernel<T, NL, NP>, dim3(grid), dim3(MS_THREADS), static_cast<size_t>(MS_SMEM), st, a);
   return static_cast<int>(cudaGetLastError());
 }

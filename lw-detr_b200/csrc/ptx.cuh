@@ -267,6 +267,28 @@ __device__ __forceinline__ uint64_t f2_mul(uint64_t a, uint64_t b) {
   return d;
 }
 
+// 2^(s*c - m) for a PAIR of scores without the MUFU (the exp-bound attention kernels move a fraction of their exponentials
+// to the FMA pipe): t = round(s*c - m) + 1.5*2^23 by one FFMA2, the fraction f = s*c - m - round(..) in [-0.5, 0.5] by
+// two more, a degree-3 polynomial for 2^f (max relative error 7.5e-5, an order of magnitude below the 16-bit rounding
+// of P) and the integer part added into the exponent field.  The raw scores are clamped at smin = (m - 125)/c first:
+// below that 2^x is 0 for every purpose here, and an unclamped argument would wrap the exponent field.
+__device__ __forceinline__ void exp2_poly2(float s0, float s1, float smin, uint64_t c2, uint64_t magic_minus_m2, uint64_t negm2, float& e0, float& e1) {
+  constexpr float kMagic = 12582912.f;   // 1.5 * 2^23
+  const uint64_t s2 = f2_pack(fmaxf(s0, smin), fmaxf(s1, smin));
+  const uint64_t t2 = f2_fma(s2, c2, magic_minus_m2);
+  const uint64_t r2 = f2_add(t2, f2_pack(-kMagic, -kMagic));
+  const uint64_t u2 = f2_fma(r2, f2_pack(-1.f, -1.f), negm2);
+  const uint64_t f2 = f2_fma(s2, c2, u2);
+  uint64_t p2 = f2_fma(f2, f2_pack(0.05517164617776871f, 0.05517164617776871f), f2_pack(0.2426111251115799f, 0.2426111251115799f));
+  p2 = f2_fma(p2, f2, f2_pack(0.6932609677314758f, 0.6932609677314758f));
+  p2 = f2_fma(p2, f2, f2_pack(0.9999280571937561f, 0.9999280571937561f));
+  float p0, p1, t0, t1;
+  f2_unpack(p2, p0, p1);
+  f2_unpack(t2, t0, t1);
+  e0 = __int_as_float(__float_as_int(p0) + (__float_as_int(t0) << 23));
+  e1 = __int_as_float(__float_as_int(p1) + (__float_as_int(t1) << 23));
+}
+
 // ----------------------------------------------------------------------------- 16/32-byte global access
 struct __align__(16) U4 { uint32_t x, y, z, w; };
 struct __align__(32) U8 { uint32_t v[8]; };

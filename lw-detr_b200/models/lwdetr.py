@@ -101,6 +101,14 @@ class LWDETR(nn.Module):
         'enc_outputs'} as fp32 CUDA tensors (lwdetr.py:161-174)."""
         if self.training:
             raise RuntimeError("lwdetr_b200 implements the inference forward only; call model.eval()")
+        if isinstance(samples, torch.Tensor) and samples.dtype == torch.uint8:
+            # raw camera / decoder frames [B, S, S, 3] (HWC, RGB, 0..255): the reference's host-side pre-processing
+            # (demo.py:146-159: /255, Normalize(mean, std), HWC -> CHW) is fused into the patch-embed load on the device
+            dev = next(self.parameters()).device
+            if dev.type != "cuda":
+                raise RuntimeError("lwdetr_b200: move the model to a CUDA device (no CPU fallback)")
+            out = self.engine().forward(samples.to(dev), want_aux=True)
+            return self._pack_outputs(out)
         if isinstance(samples, (list, torch.Tensor)):
             samples = nested_tensor_from_tensor_list(samples)
         x, mask = samples.tensors, samples.mask
@@ -122,6 +130,9 @@ class LWDETR(nn.Module):
         # the padding mask only matters when something IS padded (misc.py:317-339); an all-False mask takes the constant tables
         mask = mask.to(dev) if (mask is not None and bool(mask.any())) else None
         out = self.engine().forward(x, want_aux=True, mask=mask)
+        return self._pack_outputs(out)
+
+    def _pack_outputs(self, out):
         if self._export:
             return out["pred_boxes"], out["pred_logits"]      # forward_export tuple (lwdetr.py:176-195)
         res = {"pred_logits": out["pred_logits"], "pred_boxes": out["pred_boxes"]}
