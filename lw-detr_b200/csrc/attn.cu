@@ -422,12 +422,13 @@ int attention_tc_launch(int dtype, const AttnArgs& a, int dh, int C, cudaStream_
 int attention_slots_launch(int dtype, const AttnArgs& a, int dh, int C, cudaStream_t st);   // attn_slots.cu
 
 // Slot kernel (attn_slots.cu: tcgen05, one thread per row, partly polynomial exp2) for packed qkv:
-//   0 = never, 1 (default) = head dim 16 always + head dim 32 for sequences of <= 128 tokens (the ViT windows),
-//   2 = head dim 32 for every sequence length as well.  Environment override for A/B measurements only.
+//   0 = never, 1 = head dim 16 always + head dim 32 for sequences of <= 128 tokens (the ViT windows),
+//   2 (default) = head dim 32 for every sequence length as well (global attention, B200, isolated: medium B=64 612 us against
+//   825 us of the attn_tc.cu kernel, large B=32 334 against 424).  Environment override for A/B measurements only.
 static int slots_policy() {
   static int v = [] {
     const char* e = getenv("LWDETR_B200_ATTN_SLOTS");
-    return e ? atoi(e) : 1;
+    return e ? atoi(e) : 2;
   }();
   return v;
 }

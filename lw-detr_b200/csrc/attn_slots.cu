@@ -346,6 +346,33 @@ __global__ void __launch_bounds__(THREADS, 1) attn_slots_kernel(const __grid_con
     seq = sh / p.heads;
     return true;
   };
+  // Walking items first, first + stride, ... without a division per item (independent slots: three divisions per item in
+  // every softmax thread and driver cursor were a measurable share of the 2-chunk window items): the stride is decomposed
+  // once into (sequences, heads, query tiles) and added with carries.  The lock-step mode keeps the plain decode.
+  struct ItemIt {
+    int seq, head, qtile;
+  };
+  int st_seq = 0, st_head = 0, st_qt = 0;
+  if (!SHARED) {
+    const int per_seq = p.heads * p.qtiles, str = static_cast<int>(gridDim.x) * SLOTS;
+    st_seq = str / per_seq;
+    const int rem = str - st_seq * per_seq;
+    st_head = rem / p.qtiles;
+    st_qt = rem - st_head * p.qtiles;
+  }
+  auto it_advance = [&](ItemIt& it) {
+    it.qtile += st_qt;
+    if (it.qtile >= p.qtiles) {
+      it.qtile -= p.qtiles;
+      ++it.head;
+    }
+    it.head += st_head;
+    if (it.head >= p.heads) {
+      it.head -= p.heads;
+      ++it.seq;
+    }
+    it.seq += st_seq;
+  };
   // CTA items (SHARED) / slot items (independent slots) of slot sl: first, first + stride, ...
   auto first_of = [&](int sl) { return SHARED ? static_cast<int>(blockIdx.x) : static_cast<int>(blockIdx.x) * SLOTS + sl; };
   const int stride = SHARED ? static_cast<int>(gridDim.x) : static_cast<int>(gridDim.x) * SLOTS;
@@ -404,16 +431,24 @@ __global__ void __launch_bounds__(THREADS, 1) attn_slots_kernel(const __grid_con
       static_assert(LSTEP < STAGES, "one wrap per step");
       uint32_t l_f = SHARED ? static_cast<uint32_t>(slot) : 0u, l_st = l_f, l_ph = 0;
       int l_i = 0, l_j = static_cast<int>(l_f), l_row = 0, l_col = 0;
+      ItemIt l_it{0, 0, 0}, q_it{0, 0, 0};
+      if (!SHARED && n_my > 0) {
+        decode(first, slot, l_it.seq, l_it.head, l_it.qtile);
+        q_it = l_it;
+      }
       auto l_seek = [&]() {                                          // normalise (l_i, l_j) and look up the item's K/V rows
         while (l_j >= nchunks) {
           l_j -= nchunks;
           ++l_i;
+          if (!SHARED) it_advance(l_it);
         }
         if (l_i < n_my) {
-          int seq, head, qt;
-          decode(first + l_i * stride, slot, seq, head, qt);
-          l_row = seq * p.seqlen;
-          l_col = head * DH;
+          if (SHARED) {
+            int qt;
+            decode(first + l_i * stride, slot, l_it.seq, l_it.head, qt);
+          }
+          l_row = l_it.seq * p.seqlen;
+          l_col = l_it.head * DH;
         }
       };
       l_seek();
@@ -440,7 +475,11 @@ __global__ void __launch_bounds__(THREADS, 1) attn_slots_kernel(const __grid_con
       int q_i = 0;                     // next item whose Q tile is to be requested
       auto load_next_q = [&]() {
         int seq = 0, head = 0, qt = 0;
-        while (q_i < n_my && !decode(first + q_i * stride, slot, seq, head, qt)) ++q_i;
+        if (SHARED) {
+          while (q_i < n_my && !decode(first + q_i * stride, slot, seq, head, qt)) ++q_i;
+        } else {
+          seq = q_it.seq; head = q_it.head; qt = q_it.qtile;
+        }
         if (q_i >= n_my) return;
         const uint32_t buf = aq & 1;
         if (aq >= 2) SL_WAIT(b_q_empty + 8 * buf, ((aq >> 1) - 1) & 1);
@@ -448,6 +487,7 @@ __global__ void __launch_bounds__(THREADS, 1) attn_slots_kernel(const __grid_con
         tma_2d_a(a_q + buf * G::Q_BYTES, &tmQ, b_q_full + 8 * buf, head * DH, seq * p.seqlen + qt * BM);
         ++aq;
         ++q_i;
+        if (!SHARED) it_advance(q_it);
       };
 
       int sj = 0, si = 0, pj = 0, pi = 0;
@@ -538,9 +578,30 @@ __global__ void __launch_bounds__(THREADS, 1) attn_slots_kernel(const __grid_con
     const uint32_t b_o_full = a_o_full + 8 * slot, b_o_free = a_o_free + 8 * slot;
     const bool elected = lane == 0;
     uint32_t n_c = 0, n_item = 0;
+    ItemIt s_it{0, 0, 0};
+    if (!SHARED && first < p.nitems) decode(first, slot, s_it.seq, s_it.head, s_it.qtile);
     for (int item = first; item < p.nitems; item += stride) {
       int seq, head, qtile;
-      if (!decode(item, slot, seq, head, qtile)) continue;
+      if (SHARED) {
+        if (!decode(item, slot, seq, head, qtile)) continue;
+      } else {
+        seq = s_it.seq; head = s_it.head; qtile = s_it.qtile;
+        it_advance(s_it);
+      }
+      // A warp whose 32 rows all lie beyond the sequence (the second half of the last 128-row tile of a 1600-token sequence:
+      // 2 of 52 warp-tiles) only keeps the barrier protocol going: no TMEM traffic, no exponentials, nothing stored.
+      if (qtile * BM + quarter * 32 >= p.seqlen) {
+        for (int j = 0; j < nchunks; ++j, ++n_c) {
+          SL_WAIT(b_s_full, n_c & 1);
+          if (elected) arrive_a(b_s_free);
+          if (n_c > 0) SL_WAIT(b_p_empty, (n_c - 1) & 1);
+          if (elected) arrive_a(b_p_full);
+        }
+        SL_WAIT(b_o_full, n_item & 1);
+        if (elected) arrive_a(b_o_free);
+        ++n_item;
+        continue;
+      }
       float m_ref = -INFINITY;
       uint64_t lsum2 = pk2(0.f, 0.f);
       for (int j = 0; j < nchunks; ++j, ++n_c) {

@@ -457,10 +457,12 @@ int Engine::plan(int B, std::string* err) {
     };
     auto add_ln = [&](const std::string& label, Mat x, Mat y, const std::string& nkey, float eps, long long rows, int Cn,
                       const uint8_t* flag = nullptr, int flag_mod = 0, const float* ovr = nullptr, Mat add = Mat{nullptr, 0},
-                      Mat y2 = Mat{nullptr, 0}, long long ygroup = 0, long long ystride = 0, long long yoff = 0, long long out_rows = -1) {
+                      Mat y2 = Mat{nullptr, 0}, long long ygroup = 0, long long ystride = 0, long long yoff = 0, long long out_rows = -1,
+                      const std::string& nkey3 = std::string(), Mat y3 = Mat{nullptr, 0}, float eps3 = 0.f) {
       if (pass == 0) return;
       LayerNormArgs a;
       std::memset(&a, 0, sizeof a);
+      if (y3.p) { a.w3 = w32(nkey3 + ".w"); a.b3 = w32(nkey3 + ".b"); a.eps3 = eps3; a.y3 = y3.p; a.ldy3 = y3.ld; }
       a.x = x.p; a.ldx = x.ld; a.y = y.p; a.ldy = y.ld; a.w = w32(nkey + ".w"); a.b = w32(nkey + ".b"); a.eps = eps;
       a.rows = rows; a.C = Cn; a.row_flag = flag; a.flag_mod = flag_mod > 0 ? flag_mod : 1; a.override_vec = ovr;
       a.add_src = add.p; a.ld_add = add.ld; a.y2 = y2.p; a.ldy2 = y2.ld; a.y_group = ygroup; a.y_group_stride = ystride; a.y_row_off = yoff;
@@ -469,7 +471,7 @@ int Engine::plan(int B, std::string* err) {
       P_.label = label;
       P_.run = [a, dt](cudaStream_t st) { return layernorm_launch(dt, a, st); };
       P_.out = y.p; P_.rows = out_rows >= 0 ? out_rows : rows; P_.cols = Cn; P_.ld = y.ld;
-      P_.bytes = 4.0 * rows * Cn + (y2.p ? 4.0 * rows * Cn : 0.0);
+      P_.bytes = 4.0 * rows * Cn + (y2.p ? 4.0 * rows * Cn : 0.0) + (y3.p ? 2.0 * rows * Cn : 0.0);
       ops_.push_back(P_);
     };
     auto add_attn = [&](const std::string& label, Mat q, Mat k, Mat v, Mat o, int nseq, int seqlen, int nheads, int dh) {
@@ -694,10 +696,10 @@ int Engine::plan(int B, std::string* err) {
       add_ln(lb + ".norm2", t1, tb, k + "n2", 1e-5f, BQ, d);
       { GemmOpt o; o.act = ACT_RELU; add_gemm(lb + ".linear1", tb, BQ, d, k + "l1", ff, ffh.p, ffh.ld, o); }
       { GemmOpt o; o.resid = tb; add_gemm(lb + ".linear2", ffh, BQ, ff, k + "l2", d, t1.p, t1.ld, o); }
-      add_ln(lb, t1, tgt, k + "n3", 1e-5f, BQ, d, nullptr, 0, nullptr, qpos, tq);
-      cur = tgt;
+      // norm3 and the decoder's output norm of this layer's hidden state (transformer.py:279-285) in one launch
       Mat hsl{cptr(hs.p) + static_cast<size_t>(i) * BQ * d * 2, d};
-      add_ln(lb + ".hs", tgt, hsl, "dec_norm", 1e-5f, BQ, d);
+      add_ln(lb, t1, tgt, k + "n3", 1e-5f, BQ, d, nullptr, 0, nullptr, qpos, tq, 0, 0, 0, -1, "dec_norm", hsl, 1e-5f);
+      cur = tgt;
     }
     // ================================================================ heads
     float* logits = buf32(NL * BQ * ldc);

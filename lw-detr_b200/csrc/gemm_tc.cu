@@ -281,6 +281,25 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const long long res_row = p.resid_mod > 0 ? (m % p.resid_mod) : m;
       const bool zero_row = GEN && p.row_zero != nullptr && valid && __ldg(p.row_zero + m) != 0;
 
+      // L1 prefetch of what the NEXT tile's epilogue reads first - its rows' LayerNorm statistics and the head of its residual
+      // slice: ncu (profiles/r02j_ncu_gemm_small.txt) showed the first use of the statistics as the hottest line of the LN
+      // consumers (13 % of all samples on one FADD waiting for the load), i.e. an L2 round trip exposed once per tile.
+      if (p.a_mode == AMODE_PLAIN && pt + npairs < num_ptiles) {
+        const TileCoord tn = decode_tile(p, pt + npairs, static_cast<int>(rank), BN);
+        const long long mn = static_cast<long long>(tn.m_tile) * BM + r;
+        if (mn < p.M) {
+          if (ln_in) {
+            const char* sp = reinterpret_cast<const char*>(p.stats_in + mn * p.stats_parts_in);
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(sp));
+            if (p.stats_parts_in > 8) asm volatile("prefetch.global.L1 [%0];" ::"l"(sp + 64));
+          }
+          if (has_resid) {
+            const long long rn = p.resid_mod > 0 ? (mn % p.resid_mod) : mn;
+            const T* rp = reinterpret_cast<const T*>(p.resid) + rn * p.ld_resid + tn.n0 + chalf * (BN / 16 / (EPI_WARPS / 4)) * 16;
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(rp));
+          }
+        }
+      }
       const int npad = p.n_tiles * BN;
       const float* s_bias = s_vec + n0;
       const float* s_gamma = s_vec + npad + n0;

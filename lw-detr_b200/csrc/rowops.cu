@@ -104,6 +104,15 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const LayerNormArgs p) {
         o.x = Cvt<T>::pack(o8[0], o8[1]); o.y = Cvt<T>::pack(o8[2], o8[3]);
         o.z = Cvt<T>::pack(o8[4], o8[5]); o.w = Cvt<T>::pack(o8[6], o8[7]);
         *reinterpret_cast<U4*>(y + c * 8) = o;
+        if (p.y3 != nullptr) {                      // keep the rounded y for the chained LayerNorm below
+          const uint32_t w4[4] = {o.x, o.y, o.z, o.w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float2 f = Cvt<T>::unpack(w4[j]);
+            v[r][i][2 * j] = f.x;
+            v[r][i][2 * j + 1] = f.y;
+          }
+        }
         if (p.y2 != nullptr) {
           const T* a = reinterpret_cast<const T*>(p.add_src) + row * p.ld_add + c * 8;
           const U4 u = *reinterpret_cast<const U4*>(a);
@@ -118,6 +127,46 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const LayerNormArgs p) {
           }
           U4 oo; oo.x = o2[0]; oo.y = o2[1]; oo.z = o2[2]; oo.w = o2[3];
           *reinterpret_cast<U4*>(reinterpret_cast<T*>(p.y2) + row * p.ldy2 + c * 8) = oo;
+        }
+      }
+    }
+    if (p.y3 != nullptr) {
+      // chained LayerNorm of the rounded y (exactly what a separate launch reading y would compute)
+      float s3 = 0.f;
+#pragma unroll
+      for (int i = 0; i < CHUNKS; ++i)
+        if (lane + i * 32 < nchunk) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) s3 += v[r][i][j];
+        }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) s3 += __shfl_xor_sync(0xffffffffu, s3, o);
+      const float mean3 = s3 / p.C;
+      float q3 = 0.f;
+#pragma unroll
+      for (int i = 0; i < CHUNKS; ++i)
+        if (lane + i * 32 < nchunk) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float dd = v[r][i][j] - mean3;
+            q3 += dd * dd;
+          }
+        }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) q3 += __shfl_xor_sync(0xffffffffu, q3, o);
+      const float rstd3 = rsqrtf(q3 / p.C + p.eps3);
+      T* y3 = reinterpret_cast<T*>(p.y3) + row * p.ldy3;
+#pragma unroll
+      for (int i = 0; i < CHUNKS; ++i) {
+        const int c = lane + i * 32;
+        if (c < nchunk) {
+          float o8[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o8[j] = (v[r][i][j] - mean3) * rstd3 * __ldg(p.w3 + c * 8 + j) + __ldg(p.b3 + c * 8 + j);
+          U4 o;
+          o.x = Cvt<T>::pack(o8[0], o8[1]); o.y = Cvt<T>::pack(o8[2], o8[3]);
+          o.z = Cvt<T>::pack(o8[4], o8[5]); o.w = Cvt<T>::pack(o8[6], o8[7]);
+          *reinterpret_cast<U4*>(y3 + c * 8) = o;
         }
       }
     }

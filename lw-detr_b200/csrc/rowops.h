@@ -15,6 +15,8 @@ struct LayerNormArgs {
   const uint8_t* row_flag; int flag_mod; const float* override_vec;   // optional masked-row override
   const void* add_src; int ld_add; void* y2; int ldy2;                // optional y2 = y + add_src
   long long y_group, y_group_stride, y_row_off;   // y_group > 0: y row = (r / y_group) * y_group_stride + y_row_off + r % y_group
+  // optional chained second LayerNorm of the ROUNDED y (decoder: hs = dec_norm(tgt), transformer.py:279-285): y3 = LN(y; w3, b3, eps3)
+  const float* w3; const float* b3; float eps3; void* y3; int ldy3;
 };
 int layernorm_launch(int dtype, const LayerNormArgs& a, cudaStream_t st);
 

@@ -205,6 +205,29 @@ def test_uint8_input_equals_normalised_float_input():
     eng.close()
 
 
+def test_module_call_accepts_uint8_frames():
+    """The public nn.Module call takes what demo.py holds before its host-side transforms - uint8 [B, 640, 640, 3] frames -
+    and gives the predictions of the normalised fp32 tensor path (the e2e arm of bench.py uploads exactly this)."""
+    from b200 import capi
+    from b200.config import CONFIGS
+    from b200.synth import synth_state_dict
+    from models.lwdetr import LWDETR
+    cfg = CONFIGS["tiny"]
+    model = LWDETR(cfg, compute_dtype=torch.float16).eval()
+    model.load_state_dict(synth_state_dict(cfg, 1), strict=True)
+    model.cuda()
+    g = torch.Generator().manual_seed(1)
+    u8 = torch.randint(0, 256, (2, 640, 640, 3), generator=g, dtype=torch.uint8)
+    mean, std = torch.tensor(capi.IMAGENET_MEAN), torch.tensor(capi.IMAGENET_STD)
+    f32 = ((u8.float() / 255.0 - mean) / std).permute(0, 3, 1, 2).contiguous()
+    a = {k: v.clone() for k, v in model(f32.cuda()).items() if k.startswith("pred")}
+    b = model(u8.cuda())
+    assert set(b) == {"pred_logits", "pred_boxes", "aux_outputs", "enc_outputs"}
+    assert torch.equal(a["pred_logits"], b["pred_logits"]) and torch.equal(a["pred_boxes"], b["pred_boxes"])
+    with pytest.raises(RuntimeError):
+        model(torch.zeros(2, 3, 640, 640, dtype=torch.uint8).cuda())       # uint8 must be HWC
+
+
 def test_export_tuple_equals_dict_outputs():
     """LWDETR.export() (lwdetr.py:103-109): forward becomes forward_export and returns (pred_boxes, pred_logits) of the last
     decoder layer for a plain [B,3,H,W] tensor - the reference's contract, pinned on the CPU by
