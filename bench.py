@@ -345,6 +345,7 @@ def measure_config(cfg_name, batch, dtype_name, steps, warmup, dev, rank, world,
     hl = [torch.empty(batch, cfg.num_queries, cfg.num_classes, dtype=torch.float32).pin_memory() for _ in range(2)]
     hb = [torch.empty(batch, cfg.num_queries, 4, dtype=torch.float32).pin_memory() for _ in range(2)]
     copy_stream = torch.cuda.Stream(device=dev)
+    out_stream = torch.cuda.Stream(device=dev)
     main_stream = torch.cuda.current_stream(dev)
 
     def e2e_measure(kind):
@@ -356,6 +357,7 @@ def measure_config(cfg_name, batch, dtype_name, steps, warmup, dev, rank, world,
         dbuf = [torch.empty_like(host[0], device=dev) for _ in range(2)]
         ready = [torch.cuda.Event() for _ in range(2)]
         freed = [torch.cuda.Event() for _ in range(2)]
+        done = [torch.cuda.Event() for _ in range(2)]
 
         def upload(i):
             s_ = i & 1
@@ -375,8 +377,16 @@ def measure_config(cfg_name, batch, dtype_name, steps, warmup, dev, rank, world,
                 main_stream.wait_event(ready[s_])
                 out = model(dbuf[s_])
                 freed[s_].record(main_stream)
-                hl[s_].copy_(out["pred_logits"], non_blocking=True)
-                hb[s_].copy_(out["pred_boxes"], non_blocking=True)
+                # predictions -> pinned host on a third stream: the next forward does not queue behind the read-back (every
+                # forward writes freshly allocated output tensors, so nothing is overwritten while the copy runs)
+                done[s_].record(main_stream)
+                with torch.cuda.stream(out_stream):
+                    out_stream.wait_event(done[s_])
+                    hl[s_].copy_(out["pred_logits"], non_blocking=True)
+                    hb[s_].copy_(out["pred_boxes"], non_blocking=True)
+                    out["pred_logits"].record_stream(out_stream)
+                    out["pred_boxes"].record_stream(out_stream)
+            main_stream.wait_stream(out_stream)                    # the timed region ends when the last read-back has landed
 
         run(3)
         barrier()

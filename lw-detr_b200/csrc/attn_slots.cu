@@ -251,7 +251,7 @@ struct Geo {
   static constexpr uint32_t SLOT_COLS = 128;                   // S 64 | P 32 | O DH (<= 32): four slots fill the 512 columns
 };
 
-template <typename T, int DH, bool SHARED, uint32_t PMASK, bool FUSED>
+template <typename T, int DH, bool SHARED, uint32_t PMASK, bool FUSED, bool LONG>   // LONG: sequences of more than one 128-row tile
 __global__ void __launch_bounds__(THREADS, 1) attn_slots_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
                                                                 const SlotArgs p) {
   using G = Geo<DH, SHARED>;
@@ -580,6 +580,49 @@ __global__ void __launch_bounds__(THREADS, 1) attn_slots_kernel(const __grid_con
     uint32_t n_c = 0, n_item = 0;
     ItemIt s_it{0, 0, 0};
     if (!SHARED && first < p.nitems) decode(first, slot, s_it.seq, s_it.head, s_it.qtile);
+    // The epilogue of an item (wait for its last P V, read O and the row sum, store) is DEFERRED into the first chunk of the
+    // slot's next item, between that chunk's exponentials and its P store: the P V round trip (driver wake-up + 4 MMAs +
+    // commit, ~600 clk; 10 % of all samples of the 2-chunk window items sat in that wait) then hides behind exponentials.
+    // Measured (isolated, L2 flushed): windows 51.2 -> 49.2 us (small), 112 -> 98 us (medium), 63.5 -> 57.4 us (large); the
+    // long sequences lose 5 % to the extra live registers, so they keep the immediate epilogue (LONG).
+    bool pend = false, pend_store = false;
+    T* pend_dst = nullptr;
+    uint64_t pend_lsum2 = 0;
+    auto finish_item = [&]() {                                     // O / l -> global for the pending item
+      SL_WAIT(b_o_full, n_item & 1);
+      tc_fence_after();
+      float inv;
+      if (SUMS) {
+        float l8[8];
+        __syncwarp();
+        tmem_ld_x8(tbase + COL_L, l8);                              // 16 identical columns: the row sum of the rounded P
+        tmem_ld_wait();
+        inv = 1.f / l8[0];
+      } else {
+        float l0, l1;
+        upk2(pend_lsum2, l0, l1);
+        inv = 1.f / (l0 + l1);
+      }
+      U8 ov[DH / 16];
+#pragma unroll
+      for (int cc = 0; cc < DH / 16; ++cc) {
+        float o16[16];
+        __syncwarp();
+        tmem_ld_x16(tbase + COL_O + cc * 16, o16);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 8; ++i) ov[cc].v[i] = Cvt<T>::pack(o16[2 * i] * inv, o16[2 * i + 1] * inv);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (elected) arrive_a(b_o_free);
+      ++n_item;
+      if (pend_store) {
+#pragma unroll
+        for (int cc = 0; cc < DH / 16; ++cc) stg256(pend_dst + cc * 16, ov[cc]);
+      }
+      pend = false;
+    };
     for (int item = first; item < p.nitems; item += stride) {
       int seq, head, qtile;
       if (SHARED) {
@@ -590,7 +633,8 @@ __global__ void __launch_bounds__(THREADS, 1) attn_slots_kernel(const __grid_con
       }
       // A warp whose 32 rows all lie beyond the sequence (the second half of the last 128-row tile of a 1600-token sequence:
       // 2 of 52 warp-tiles) only keeps the barrier protocol going: no TMEM traffic, no exponentials, nothing stored.
-      if (qtile * BM + quarter * 32 >= p.seqlen) {
+      if (LONG && qtile * BM + quarter * 32 >= p.seqlen) {
+        if (pend) finish_item();
         for (int j = 0; j < nchunks; ++j, ++n_c) {
           SL_WAIT(b_s_full, n_c & 1);
           if (elected) arrive_a(b_s_free);
@@ -689,6 +733,7 @@ __global__ void __launch_bounds__(THREADS, 1) attn_slots_kernel(const __grid_con
         // only now wait for PV(j-1): its latency hides behind the exponentials above (P is single-buffered)
         if (n_c > 0) SL_WAIT(b_p_empty, (n_c - 1) & 1);
         tc_fence_after();
+        if (!LONG && j == 0 && pend) finish_item();                 // the previous item's last P V is complete at this point
         if (j > 0 && __any_sync(0xffffffffu, move)) {               // rare after the first chunks: rescale this row of O (and of l)
 #pragma unroll
           for (int cc = 0; cc < (DH + (SUMS ? 16 : 0)) / 16; ++cc) {
@@ -709,42 +754,15 @@ __global__ void __launch_bounds__(THREADS, 1) attn_slots_kernel(const __grid_con
         __syncwarp();
         if (elected) arrive_a(b_p_full);
       }
-      // ---- O / l -> global
-      SL_WAIT(b_o_full, n_item & 1);
-      tc_fence_after();
-      float inv;
-      if (SUMS) {
-        float l8[8];
-        __syncwarp();
-        tmem_ld_x8(tbase + COL_L, l8);                              // 16 identical columns: the row sum of the rounded P
-        tmem_ld_wait();
-        inv = 1.f / l8[0];
-      } else {
-        float l0, l1;
-        upk2(lsum2, l0, l1);
-        inv = 1.f / (l0 + l1);
-      }
+      // ---- the item's epilogue is deferred (see finish_item above)
       const int qrow = qtile * BM + r;
-      T* dst = reinterpret_cast<T*>(p.o) + (static_cast<long long>(seq) * p.seqlen + qrow) * p.ldo + head * DH;
-      U8 ov[DH / 16];
-#pragma unroll
-      for (int cc = 0; cc < DH / 16; ++cc) {
-        float o16[16];
-        __syncwarp();
-        tmem_ld_x16(tbase + COL_O + cc * 16, o16);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 8; ++i) ov[cc].v[i] = Cvt<T>::pack(o16[2 * i] * inv, o16[2 * i + 1] * inv);
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (elected) arrive_a(b_o_free);
-      ++n_item;
-      if (qrow < p.seqlen) {
-#pragma unroll
-        for (int cc = 0; cc < DH / 16; ++cc) stg256(dst + cc * 16, ov[cc]);
-      }
+      pend_dst = reinterpret_cast<T*>(p.o) + (static_cast<long long>(seq) * p.seqlen + qrow) * p.ldo + head * DH;
+      pend_store = qrow < p.seqlen;
+      pend_lsum2 = lsum2;
+      pend = true;
+      if (LONG) finish_item();        // 13+ chunks per item amortise the round trip; deferring only costs registers there (measured)
     }
+    if (pend) finish_item();
   }
   tc_fence_before();
   __syncthreads();
@@ -770,7 +788,7 @@ static WaitDbg* debug_buffer() {
   return dev;
 }
 
-template <typename T, int DH, bool SHARED, uint32_t PMASK, bool FUSED>
+template <typename T, int DH, bool SHARED, uint32_t PMASK, bool FUSED, bool LONG>
 static int launch_m(const AttnArgs& a, int C, cudaStream_t st) {
   using G = Geo<DH, SHARED>;
   CUtensorMap tq, tkv;
@@ -793,10 +811,10 @@ static int launch_m(const AttnArgs& a, int C, cudaStream_t st) {
   // One CTA per SM (it allocates all 512 TMEM columns): more than half of the shared memory is requested so that a second
   // CTA can never become resident and spin inside tcgen05.alloc.
   const size_t smem = std::max<size_t>(G::SMEM, 116 * 1024);
-  if (int e = ensure_max_dyn_smem(reinterpret_cast<const void*>(attn_slots_kernel<T, DH, SHARED, PMASK, FUSED>), 227 * 1024)) return e;
+  if (int e = ensure_max_dyn_smem(reinterpret_cast<const void*>(attn_slots_kernel<T, DH, SHARED, PMASK, FUSED, LONG>), 227 * 1024)) return e;
   const long long ctas = SHARED ? nitems : (nitems + SLOTS - 1) / SLOTS;
   const unsigned grid = static_cast<unsigned>(std::min<long long>(ctas, current_device_sms()));
-  launch_k(attn_slots_kernel<T, DH, SHARED, PMASK, FUSED>, dim3(grid), dim3(THREADS), smem, st, tq, tkv, p);
+  launch_k(attn_slots_kernel<T, DH, SHARED, PMASK, FUSED, LONG>, dim3(grid), dim3(THREADS), smem, st, tq, tkv, p);
   return static_cast<int>(cudaGetLastError());
 }
 
@@ -826,11 +844,17 @@ static int slots_mode() {
 template <typename T, int DH, uint32_t PMASK>
 static int launch_p(const AttnArgs& a, int C, cudaStream_t st) {
   const int mode = slots_mode();
-  const bool indep = a.seqlen <= BM || (mode & 1);
-  if constexpr (DH == 16) {
-    if (mode & 2) return indep ? launch_m<T, DH, false, PMASK, true>(a, C, st) : launch_m<T, DH, true, PMASK, true>(a, C, st);
+  if (a.seqlen <= BM) {                              // one tile per sequence (the 100-token windows): independent slots
+    if constexpr (DH == 16) {
+      if (mode & 2) return launch_m<T, DH, false, PMASK, true, false>(a, C, st);
+    }
+    return launch_m<T, DH, false, PMASK, false, false>(a, C, st);
   }
-  return indep ? launch_m<T, DH, false, PMASK, false>(a, C, st) : launch_m<T, DH, true, PMASK, false>(a, C, st);
+  const bool indep = (mode & 1) != 0;
+  if constexpr (DH == 16) {
+    if (mode & 2) return indep ? launch_m<T, DH, false, PMASK, true, true>(a, C, st) : launch_m<T, DH, true, PMASK, true, true>(a, C, st);
+  }
+  return indep ? launch_m<T, DH, false, PMASK, false, true>(a, C, st) : launch_m<T, DH, true, PMASK, false, true>(a, C, st);
 }
 
 template <typename T, int DH>

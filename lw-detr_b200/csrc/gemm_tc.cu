@@ -245,8 +245,47 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     int it = 0;
     const int n_my_tiles = pair < num_ptiles ? (num_ptiles - pair + npairs - 1) / npairs : 0;
+    // Tile walk without a division per tile (plain GEMMs; ncu counted ~180 of the 324 instructions a warp spends per qkv tile
+    // in tile decoding, row bookkeeping and the statistics reduction - more than on its 48 output columns): pair-tile index
+    // pt = m_pair * n_tiles + n_tile advances by npairs = d_mp * n_tiles + d_nt with a carry.
+    const bool plain = p.a_mode == AMODE_PLAIN;
+    const int d_mp = npairs / p.n_tiles, d_nt = npairs - d_mp * p.n_tiles;
+    int w_nt = pair % p.n_tiles, w_mp = pair / p.n_tiles;
+    auto plain_tile = [&](int nt, int mp) {
+      TileCoord t;
+      t.n_tile = nt;
+      t.m_tile = 2 * mp + static_cast<int>(rank);
+      t.n0 = nt * BN;
+      t.cb = t.cy0 = t.cx0 = 0;
+      return t;
+    };
+    // LayerNorm statistics of a row: the producer's partial (sum, sum of squares) pairs.  The partials of the NEXT tile's rows
+    // are requested at the start of a tile and reduced at its end (first four in registers), so the L2 round trip that used to
+    // stall the first use (13 % of all samples of the qkv GEMM on one FADD) overlaps the tile's own work.
+    float nx_mean = 0.f, nx_rstd = 1.f;
+    auto stats_of = [&](long long mrow, float& mean, float& rstd) {
+      float s1 = 0.f, s2 = 0.f;
+      for (int i = 0; i < p.stats_parts_in; ++i) {
+        const float2 q = __ldg(p.stats_in + mrow * p.stats_parts_in + i);
+        s1 += q.x;
+        s2 += q.y;
+      }
+      mean = s1 * p.ln_inv_c;
+      rstd = rsqrtf(fmaxf(s2 * p.ln_inv_c - mean * mean, 0.f) + p.ln_eps);
+    };
+    if (ln_in && plain && pair < num_ptiles) {
+      const long long m0 = static_cast<long long>(2 * w_mp + static_cast<int>(rank)) * BM + r;
+      if (m0 < p.M) stats_of(m0, nx_mean, nx_rstd);
+    }
     for (int pt = pair; pt < num_ptiles; pt += npairs, ++it) {
-      const TileCoord tc = decode_tile(p, pt, static_cast<int>(rank), BN);
+      const TileCoord tc = plain ? plain_tile(w_nt, w_mp) : decode_tile(p, pt, static_cast<int>(rank), BN);
+      // next tile of this CTA
+      w_nt += d_nt;
+      w_mp += d_mp;
+      if (w_nt >= p.n_tiles) {
+        w_nt -= p.n_tiles;
+        ++w_mp;
+      }
       const int n0 = tc.n0;
       const int buf = it & 1;
       int m, b = 0, y = 0, x = 0;
@@ -281,40 +320,28 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const long long res_row = p.resid_mod > 0 ? (m % p.resid_mod) : m;
       const bool zero_row = GEN && p.row_zero != nullptr && valid && __ldg(p.row_zero + m) != 0;
 
-      // L1 prefetch of what the NEXT tile's epilogue reads first - its rows' LayerNorm statistics and the head of its residual
-      // slice: ncu (profiles/r02j_ncu_gemm_small.txt) showed the first use of the statistics as the hottest line of the LN
-      // consumers (13 % of all samples on one FADD waiting for the load), i.e. an L2 round trip exposed once per tile.
-      if (p.a_mode == AMODE_PLAIN && pt + npairs < num_ptiles) {
-        const TileCoord tn = decode_tile(p, pt + npairs, static_cast<int>(rank), BN);
-        const long long mn = static_cast<long long>(tn.m_tile) * BM + r;
-        if (mn < p.M) {
-          if (ln_in) {
-            const char* sp = reinterpret_cast<const char*>(p.stats_in + mn * p.stats_parts_in);
-            asm volatile("prefetch.global.L1 [%0];" ::"l"(sp));
-            if (p.stats_parts_in > 8) asm volatile("prefetch.global.L1 [%0];" ::"l"(sp + 64));
-          }
-          if (has_resid) {
-            const long long rn = p.resid_mod > 0 ? (mn % p.resid_mod) : mn;
-            const T* rp = reinterpret_cast<const T*>(p.resid) + rn * p.ld_resid + tn.n0 + chalf * (BN / 16 / (EPI_WARPS / 4)) * 16;
-            asm volatile("prefetch.global.L1 [%0];" ::"l"(rp));
-          }
-        }
-      }
       const int npad = p.n_tiles * BN;
       const float* s_bias = s_vec + n0;
       const float* s_gamma = s_vec + npad + n0;
       const float* s_csum = s_vec + 2 * npad + n0;
       // fused LayerNorm (consumer): combine the producer's partial sums of this row
       float ln_mean = 0.f, ln_rstd = 1.f;
-      if (ln_in && valid) {
-        float s1 = 0.f, s2 = 0.f;
-        for (int i = 0; i < p.stats_parts_in; ++i) {
-          const float2 q = __ldg(p.stats_in + static_cast<long long>(m) * p.stats_parts_in + i);
-          s1 += q.x;
-          s2 += q.y;
+      float2 nq[4];
+      long long nx_row = -1;
+      if (ln_in && plain) {
+        ln_mean = nx_mean;                            // reduced at the end of the previous tile (or before the loop)
+        ln_rstd = nx_rstd;
+        if (pt + npairs < num_ptiles) {
+          const long long mn = static_cast<long long>(2 * w_mp + static_cast<int>(rank)) * BM + r;
+          if (mn < p.M) {
+            nx_row = mn;
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              if (i < p.stats_parts_in) nq[i] = __ldg(p.stats_in + mn * p.stats_parts_in + i);
+          }
         }
-        ln_mean = s1 * p.ln_inv_c;
-        ln_rstd = rsqrtf(fmaxf(s2 * p.ln_inv_c - ln_mean * ln_mean, 0.f) + p.ln_eps);
+      } else if (ln_in && valid) {
+        stats_of(m, ln_mean, ln_rstd);
       }
       float st_sum = 0.f, st_sq = 0.f;
       const T* resid_row = has_resid ? reinterpret_cast<const T*>(p.resid) + res_row * p.ld_resid : nullptr;
@@ -508,6 +535,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
       if (do_stats && valid)
         p.stats_out[static_cast<long long>(m) * p.stats_parts_out + tc.n_tile * (EPI_WARPS / 4) + chalf] = make_float2(st_sum, st_sq);
+      if (nx_row >= 0) {                              // statistics of the next tile's row: the requests above have landed by now
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          if (i < p.stats_parts_in) {
+            s1 += nq[i].x;
+            s2 += nq[i].y;
+          }
+        for (int i = 4; i < p.stats_parts_in; ++i) {
+          const float2 q = __ldg(p.stats_in + nx_row * p.stats_parts_in + i);
+          s1 += q.x;
+          s2 += q.y;
+        }
+        nx_mean = s1 * p.ln_inv_c;
+        nx_rstd = rsqrtf(fmaxf(s2 * p.ln_inv_c - nx_mean * nx_mean, 0.f) + p.ln_eps);
+      }
     }
   }
 
