@@ -140,7 +140,7 @@ int lwdetr_msda_forward(int dtype, const void* value_hm, int64_t v_image_stride,
   a.value = value_hm; a.v_b_stride = v_image_stride; a.offs_logits = offs_logits; a.ld_ol = ld_ol; a.ref = ref; a.valid_ratio = valid_ratio;
   a.out = out; a.ld_out = ld_out; a.batch = B; a.nq = Lq; a.heads = M; a.levels = L; a.points = P; a.S = S;
   for (int l = 0; l < L; ++l) { a.lvl_h[l] = spatial_shapes_host[2 * l]; a.lvl_w[l] = spatial_shapes_host[2 * l + 1]; a.lvl_start[l] = level_start_host[l]; }
-  if (lwb::msda_plan(&a)) return fail("lwdetr_msda_forward: a feature level is wider than 840 tokens or there are too many bands");
+  if (lwb::msda_plan(&a)) return fail("lwdetr_msda_forward: a feature level is wider than 840 tokens, larger than 8192 tokens, or there are too many bands");
   int e = lwb::msda_launch(dtype, a, static_cast<cudaStream_t>(stream));
   if (e == -2) return fail("lwdetr_msda_forward: unsupported (levels, points) combination");
   if (e) return cuda_fail(e, "lwdetr_msda_forward launch");

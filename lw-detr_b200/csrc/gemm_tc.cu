@@ -26,7 +26,7 @@ namespace lwb {
 static constexpr int BM = 128;
 static constexpr int BK = 64;
 static constexpr int A_STAGE_BYTES = BM * BK * 2;
-static constexpr int EPI_WARPS = 16;                      // four warps per TMEM lane quarter, a quarter of the columns each
+static constexpr int EPI_WARPS = 16;                      // two groups of 8 (alternate tiles); in a group two warps per TMEM lane quarter, half of the columns each
 static constexpr int GEMM_THREADS = 64 + 32 * EPI_WARPS;
 static constexpr int MAX_STAGES = 8;
 
@@ -144,7 +144,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&acc_full[b], 1);
-      mbar_init(&acc_empty[b], 2 * EPI_WARPS);      // epilogue warps of both CTAs
+      mbar_init(&acc_empty[b], p.epi_groups == 2 ? EPI_WARPS : 2 * EPI_WARPS);   // the epilogue warps (of one group / of both) in each of the two CTAs
     }
     fence_mbar_init();
   }
@@ -221,7 +221,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   } else {
     // -------------------------------------------------------------------- epilogue (16 warps, both CTAs)
     const int quarter = warp & 3;               // TMEM lanes [32*quarter, 32*quarter+32) (hardware: warp_id % 4)
-    const int chalf = (warp - 2) >> 2;          // which slice of the tile's 16-column chunks this warp owns
+    // The 16 epilogue warps form TWO GROUPS.  With many tiles per CTA (epi_groups = 2: qkv, fc1, ...) the groups take alternate
+    // tiles (group g owns accumulator buffer g): while one group is in the latency-bound head of its tile (statistics, TMEM
+    // pull, residual) or in its stores, the other one is in its arithmetic - as one group the four warps of a scheduler moved in
+    // lock step and left the FMA pipe idle half of the time (fc1: FMA pipe 52 % busy at an FMA-bound epilogue,
+    // profiles/r02_ncu_gemm_small.txt).  Measured in the small / B = 32 step: qkv 257 -> 233 us, fc1 364 -> 353 us per 10
+    // launches.  With two or three tiles per CTA (proj, fc2, the projector) halving the warps per tile only stretches the tail
+    // (fc2 274 -> 309 us), so there both groups split every tile (epi_groups = 1: group g takes half of the pull rounds).
+    const int grp = (warp - 2) >> 3;
+    const int chalf = ((warp - 2) >> 2) & 1;    // which half of the tile's 16-column chunks this warp owns
     const int r = quarter * 32 + lane;          // row inside this CTA's 128-row tile
     constexpr bool GEN = EP == EP_GENERIC;
     const bool has_gamma = (GEN || EP == EP_RESID) && p.gamma != nullptr;
@@ -249,8 +257,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // in tile decoding, row bookkeeping and the statistics reduction - more than on its 48 output columns): pair-tile index
     // pt = m_pair * n_tiles + n_tile advances by npairs = d_mp * n_tiles + d_nt with a carry.
     const bool plain = p.a_mode == AMODE_PLAIN;
-    const int d_mp = npairs / p.n_tiles, d_nt = npairs - d_mp * p.n_tiles;
-    int w_nt = pair % p.n_tiles, w_mp = pair / p.n_tiles;
+    const bool alt = p.epi_groups == 2;
+    const int tstep = alt ? 2 * npairs : npairs;        // this group's next tile
+    const int d_mp = tstep / p.n_tiles, d_nt = tstep - d_mp * p.n_tiles;
+    const int pt0 = alt ? pair + grp * npairs : pair;
+    int w_nt = pt0 % p.n_tiles, w_mp = pt0 / p.n_tiles;
     auto plain_tile = [&](int nt, int mp) {
       TileCoord t;
       t.n_tile = nt;
@@ -273,13 +284,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       mean = s1 * p.ln_inv_c;
       rstd = rsqrtf(fmaxf(s2 * p.ln_inv_c - mean * mean, 0.f) + p.ln_eps);
     };
-    if (ln_in && plain && pair < num_ptiles) {
+    if (ln_in && plain && pt0 < num_ptiles) {
       const long long m0 = static_cast<long long>(2 * w_mp + static_cast<int>(rank)) * BM + r;
       if (m0 < p.M) stats_of(m0, nx_mean, nx_rstd);
     }
-    for (int pt = pair; pt < num_ptiles; pt += npairs, ++it) {
+    it = alt ? grp : 0;
+    const int it_step = alt ? 2 : 1;
+    for (int pt = pt0; pt < num_ptiles; pt += tstep, it += it_step) {
       const TileCoord tc = plain ? plain_tile(w_nt, w_mp) : decode_tile(p, pt, static_cast<int>(rank), BN);
-      // next tile of this CTA
+      // next tile of this group
       w_nt += d_nt;
       w_mp += d_mp;
       if (w_nt >= p.n_tiles) {
@@ -331,7 +344,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (ln_in && plain) {
         ln_mean = nx_mean;                            // reduced at the end of the previous tile (or before the loop)
         ln_rstd = nx_rstd;
-        if (pt + npairs < num_ptiles) {
+        if (pt + tstep < num_ptiles) {
           const long long mn = static_cast<long long>(2 * w_mp + static_cast<int>(rank)) * BM + r;
           if (mn < p.M) {
             nx_row = mn;
@@ -486,55 +499,48 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         return false;
       };
 
-      constexpr int CH_PER_WARP = BN / 16 / (EPI_WARPS / 4);
+      constexpr int CH_PER_WARP = BN / 16 / 2;
+      // The slice is pulled G chunks (16 columns each) at a time - the kernel runs at 96 registers per thread - and the TMEM
+      // buffer goes back to the MMA warp right after this warp's LAST pull, before that round's math / stores.
+      constexpr int G = CH_PER_WARP % 3 == 0 ? 3 : (CH_PER_WARP >= 4 ? 2 : 1);
+      constexpr int NR = CH_PER_WARP / G;               // pull rounds per column half: 4 / 2 / 2 / 2 for BN = 256 / 192 / 128 / 64
+      static_assert(CH_PER_WARP % G == 0 && NR % 2 == 0, "chunk rounds");
+      const int rd0 = alt ? 0 : grp * (NR / 2), rd1 = alt ? NR : rd0 + NR / 2;   // this warp's rounds
       const int c_first = chalf * CH_PER_WARP;
       U8 rr_cur, rr_nxt;
-      bool rv_cur = resid_prefetch(c_first, rr_cur), rv_nxt = false;
+      bool rv_cur = resid_prefetch(c_first + rd0 * G, rr_cur), rv_nxt = false;
 
       mbar_wait(&acc_full[buf], (it >> 1) & 1);
       tc_fence_after();
       const uint32_t taddr_row = tmem_base + buf * ACC_STRIDE + (static_cast<uint32_t>(quarter * 32) << 16);
-
-      // Pull this warp's accumulator slice into registers and hand the TMEM buffer back to the MMA warp BEFORE the
-      // math / stores: the tensor core starts tile it+2 while tile it is still being finished.  (18 warps put 5 on
-      // one scheduler, which caps the kernel at 96 registers/thread, so 4-chunk slices are pulled in two halves.)
-      constexpr int G0 = CH_PER_WARP <= 3 ? CH_PER_WARP : CH_PER_WARP / 2;     // chunks pulled before the release
-      float v[G0][16];
-      __syncwarp();                                   // tcgen05.ld is .sync.aligned: reconverge first
-      if constexpr (G0 < CH_PER_WARP) {
+      float v[G][16];
+#pragma unroll 1                                    // one copy of the (large) chunk code: the rounds differ only in their column offset
+      for (int rd = rd0; rd < rd1; ++rd) {
+        __syncwarp();                                 // tcgen05.ld is .sync.aligned: reconverge first
 #pragma unroll
-        for (int i = 0; i < G0; ++i) tmem_ld_x16(taddr_row + (c_first + i) * 16, v[i]);
+        for (int i = 0; i < G; ++i) tmem_ld_x16(taddr_row + (c_first + rd * G + i) * 16, v[i]);
         tmem_ld_wait();
+        if (rd == rd1 - 1) {
+          tc_fence_before();
+          __syncwarp();
+          // (the release of the last two tiles is never consumed: skipping it also guarantees that no remote arrive is
+          //  still in flight when the pair leaves through the relaxed cluster rendezvous below)
+          if (lane == 0 && it + 2 < n_my_tiles) {
+            if (rank == 0) mbar_arrive(&acc_empty[buf]);
+            else mbar_arrive_cluster(&acc_empty[buf], 0);
+          }
+        }
 #pragma unroll
-        for (int i = 0; i < G0; ++i) {
-          rv_nxt = resid_prefetch(c_first + i + 1, rr_nxt);
-          finish_chunk(c_first + i, v[i], rr_cur, rv_cur);
+        for (int i = 0; i < G; ++i) {
+          const int c = rd * G + i;
+          if (c + 1 < rd1 * G) rv_nxt = resid_prefetch(c_first + c + 1, rr_nxt);
+          finish_chunk(c_first + c, v[i], rr_cur, rv_cur);
           rr_cur = rr_nxt;
           rv_cur = rv_nxt;
         }
-        __syncwarp();
-      }
-      constexpr int C1 = G0 < CH_PER_WARP ? G0 : 0;                            // first chunk of the final group
-#pragma unroll
-      for (int i = 0; i < CH_PER_WARP - C1; ++i) tmem_ld_x16(taddr_row + (c_first + C1 + i) * 16, v[i]);
-      tmem_ld_wait();
-      tc_fence_before();
-      __syncwarp();
-      // (the release of the last two tiles is never consumed: skipping it also guarantees that no remote arrive is
-      //  still in flight when the pair leaves through the relaxed cluster rendezvous below)
-      if (lane == 0 && it + 2 < n_my_tiles) {
-        if (rank == 0) mbar_arrive(&acc_empty[buf]);
-        else mbar_arrive_cluster(&acc_empty[buf], 0);
-      }
-#pragma unroll
-      for (int i = 0; i < CH_PER_WARP - C1; ++i) {
-        if (C1 + i + 1 < CH_PER_WARP) rv_nxt = resid_prefetch(c_first + C1 + i + 1, rr_nxt);
-        finish_chunk(c_first + C1 + i, v[i], rr_cur, rv_cur);
-        rr_cur = rr_nxt;
-        rv_cur = rv_nxt;
       }
       if (do_stats && valid)
-        p.stats_out[static_cast<long long>(m) * p.stats_parts_out + tc.n_tile * (EPI_WARPS / 4) + chalf] = make_float2(st_sum, st_sq);
+        p.stats_out[static_cast<long long>(m) * p.stats_parts_out + (alt ? tc.n_tile * 2 + chalf : tc.n_tile * 4 + chalf * 2 + grp)] = make_float2(st_sum, st_sq);
       if (nx_row >= 0) {                              // statistics of the next tile's row: the requests above have landed by now
         float s1 = 0.f, s2 = 0.f;
 #pragma unroll
@@ -673,7 +679,6 @@ int gemm_build(const GemmDesc& d, GemmOp* op, std::string* err) {
   const int bn = pick_bn(d.N, m_tiles);
   op->bn = bn;
   a.n_tiles = (d.N + bn - 1) / bn;
-  a.stats_parts_out = a.n_tiles * (EPI_WARPS / 4);
   {
     const cuuint64_t dims[2] = {static_cast<cuuint64_t>(d.K), static_cast<cuuint64_t>(d.N)};
     const cuuint64_t strides[1] = {static_cast<cuuint64_t>(d.K) * 2};
@@ -690,6 +695,11 @@ int gemm_build(const GemmDesc& d, GemmOp* op, std::string* err) {
   op->smem = 1024 + static_cast<size_t>(stages) * stage_bytes + 256 + vec_bytes;
   const long long ptiles = static_cast<long long>((m_tiles + 1) / 2) * a.n_tiles;
   op->grid = 2u * static_cast<unsigned>(std::min<long long>(ptiles, num_sms() / 2));
+  // epilogue groups on alternate tiles once a CTA pair has at least six tiles to walk (see the kernel); the LayerNorm
+  // partials a producer writes per row follow: one per (n-tile, column half) or one per (n-tile, column half, group)
+  a.epi_groups = ptiles >= 6LL * (op->grid / 2) ? 2 : 1;
+  if (const char* e = getenv("LWDETR_B200_GEMM_GROUPS")) a.epi_groups = atoi(e) == 2 ? 2 : 1;   // A/B measurements
+  a.stats_parts_out = a.n_tiles * (a.epi_groups == 2 ? 2 : 4);
   op->flops = 2.0 * d.M * static_cast<double>(d.N) * d.K;
   return 0;
 }

@@ -49,6 +49,7 @@ struct GemmArgs {
   int stats_parts_in;
   const float* colsum;      // [N] fp32 (consumer)
   float ln_inv_c, ln_eps;   // 1/C of the normalised dimension, epsilon
+  int epi_groups;           // 2: the two 8-warp epilogue groups take alternate tiles (many tiles per CTA); 1: both work on every tile
 };
 
 // Host description of one GEMM.

@@ -169,8 +169,10 @@ __global__ void __launch_bounds__(MS_THREADS, 1) msda_fwd_kernel(const __grid_co
       Raw cur = nxt;
       if (pass + 1 < npass) load_raw(b, m, q + MS_QPASS, nxt);
       else if (it + 1 < n_my) load_raw(nb, nm, qt, nxt);
-      // ---- this thread's samples: image coordinates and softmax weight (0 when the sample is outside)
-      float px[SPT], py[SPT], pw[SPT];
+      // ---- this thread's samples, prepared ONCE per (item, pass) - not per band: the four corner weights (softmax weight and
+      // the zero weight of out-of-image corners folded in), the clamped corner tokens relative to the level, the sample's row
+      float wc[SPT][4];
+      uint32_t info[SPT];     // bits 0-12: token of the (clamped) top-left corner in its level, 13: x step, 14: y step, 16-31: floor(y) + 1 (0xffff: no weight)
       if (active) {
         float lg[LP];
         float mx = -INFINITY;
@@ -198,12 +200,20 @@ __global__ void __launch_bounds__(MS_THREADS, 1) msda_fwd_kernel(const __grid_co
             lx *= __ldg(p.valid_ratio + (b * NL + l) * 2);
             ly *= __ldg(p.valid_ratio + (b * NL + l) * 2 + 1);
           }
-          const float H = static_cast<float>(p.lvl_h[l]), W = static_cast<float>(p.lvl_w[l]);
-          px[k] = lx * W - 0.5f;                                           // cuh:285-286
-          py[k] = ly * H - 0.5f;
-          const bool in = py[k] > -1.f && px[k] > -1.f && py[k] < H && px[k] < W;   // cuh:288
-          const float w = sub ? lg[2 * k + 1] : lg[2 * k];
-          pw[k] = in ? w * inv : 0.f;
+          const int H = p.lvl_h[l], W = p.lvl_w[l];
+          const float px = lx * W - 0.5f, py = ly * H - 0.5f;              // cuh:285-286
+          const bool in = py > -1.f && px > -1.f && py < H && px < W;      // cuh:288
+          const float w = in ? (sub ? lg[2 * k + 1] : lg[2 * k]) * inv : 0.f;
+          const float yf = floorf(py), xf = floorf(px);
+          const int y0 = static_cast<int>(yf), x0 = static_cast<int>(xf);
+          const float fy = py - yf, fx = px - xf;
+          // clamped corner tokens (always readable), zero weight for the corners outside the image (cuh:58-84)
+          const int ya = max(y0, 0), yb = min(y0 + 1, H - 1), xa = max(x0, 0), xb = min(x0 + 1, W - 1);
+          const float wy0 = y0 >= 0 ? w - w * fy : 0.f, wy1 = y0 + 1 < H ? w * fy : 0.f;
+          const float wx0 = x0 >= 0 ? 1.f - fx : 0.f, wx1 = x0 + 1 < W ? fx : 0.f;
+          wc[k][0] = wy0 * wx0; wc[k][1] = wy0 * wx1; wc[k][2] = wy1 * wx0; wc[k][3] = wy1 * wx1;
+          info[k] = static_cast<uint32_t>(ya * W + xa) | (static_cast<uint32_t>(xb - xa) << 13) | (static_cast<uint32_t>(yb - ya) << 14) |
+                    ((w != 0.f ? static_cast<uint32_t>(y0 + 1) : 0xffffu) << 16);   // a sample without weight never matches a band
         }
       }
       uint64_t acc[8];
@@ -219,24 +229,18 @@ __global__ void __launch_bounds__(MS_THREADS, 1) msda_fwd_kernel(const __grid_co
           for (int ks = 0; ks < SPT; ++ks) {
             const int l = ks / (NP / MS_TPQ);
             if (NL > 1 && l != blvl) continue;                             // uniform
-            const int H = p.lvl_h[l], W = p.lvl_w[l];
-            const float yf = floorf(py[ks]), xf = floorf(px[ks]);
-            const int y0 = static_cast<int>(yf), x0 = static_cast<int>(xf);
-            if (pw[ks] == 0.f || y0 < own0 || y0 > own1) continue;
-            const float ly = py[ks] - yf, lx = px[ks] - xf;
-            // all four corner reads are issued unconditionally (clamped address, zero weight outside the image)
-            const int ya = max(y0, 0), yb = min(y0 + 1, H - 1), xa = max(x0, 0), xb = min(x0 + 1, W - 1);
-            const float wy0 = y0 >= 0 ? pw[ks] - pw[ks] * ly : 0.f, wy1 = y0 + 1 < H ? pw[ks] * ly : 0.f;
-            const float wx0 = x0 >= 0 ? 1.f - lx : 0.f, wx1 = x0 + 1 < W ? lx : 0.f;
-            const uint32_t ra = stage + static_cast<uint32_t>((ya - row0) * W) * 32u, rb = stage + static_cast<uint32_t>((yb - row0) * W) * 32u;
-            const uint32_t addr[4] = {ra + xa * 32, ra + xb * 32, rb + xa * 32, rb + xb * 32};
-            const float wc[4] = {wy0 * wx0, wy0 * wx1, wy1 * wx0, wy1 * wx1};
+            const int y0 = static_cast<int>(info[ks] >> 16) - 1;
+            if (y0 < own0 || y0 > own1) continue;                          // the band that holds both rows of the sample takes it
+            const int W = p.lvl_w[l];
+            const uint32_t a00 = stage + static_cast<uint32_t>(static_cast<int>(info[ks] & 0x1fffu) - row0 * W) * 32u;
+            const uint32_t ax = ((info[ks] >> 13) & 1u) * 32u, ay = ((info[ks] >> 14) & 1u) * static_cast<uint32_t>(W) * 32u;
+            const uint32_t addr[4] = {a00, a00 + ax, a00 + ay, a00 + ay + ax};
 #pragma unroll
             for (int rowp = 0; rowp < 2; ++rowp) {                         // the two corners of one image row at a time (16 registers in flight)
               const U4 v[4] = {lds16(addr[rowp * 2]), lds16(addr[rowp * 2] + 16), lds16(addr[rowp * 2 + 1]), lds16(addr[rowp * 2 + 1] + 16)};
 #pragma unroll
               for (int cx = 0; cx < 2; ++cx) {
-                const uint64_t w2 = f2_pack(wc[rowp * 2 + cx], wc[rowp * 2 + cx]);
+                const uint64_t w2 = f2_pack(wc[ks][rowp * 2 + cx], wc[ks][rowp * 2 + cx]);
 #pragma unroll
                 for (int hh = 0; hh < 2; ++hh) {
                   const U4 u = v[cx * 2 + hh];
@@ -283,7 +287,7 @@ int msda_plan(MsdaArgs* a) {
   a->nbands = 0;
   for (int l = 0; l < a->levels; ++l) {
     const int H = a->lvl_h[l], W = a->lvl_w[l];
-    if (H < 1 || W < 1 || 2 * W > MS_STAGE_TOKENS) return -2;
+    if (H < 1 || W < 1 || 2 * W > MS_STAGE_TOKENS || H * W > 8192 || H > 0xfff0) return -2;   // token / row fields of the packed sample info
     const int rows_max = MS_STAGE_TOKENS / W;                    // rows a stage holds
     if (H <= rows_max) {
       if (a->nbands >= MSDA_MAX_BANDS) return -2;
