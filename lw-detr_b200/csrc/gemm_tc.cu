@@ -274,15 +274,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // are requested at the start of a tile and reduced at its end (first four in registers), so the L2 round trip that used to
     // stall the first use (13 % of all samples of the qkv GEMM on one FADD) overlaps the tile's own work.
     float nx_mean = 0.f, nx_rstd = 1.f;
+    // combine equal-width partials (sum_p, M2_p): mean = sum(sum_p) / C, var = [sum(M2_p) + n_p * sum((sum_p / n_p - mean)^2)] / C
+    const float part_n = p.stats_parts_in > 0 ? 1.f / (p.ln_inv_c * p.stats_parts_in) : 1.f, part_inv_n = 1.f / part_n;
     auto stats_of = [&](long long mrow, float& mean, float& rstd) {
-      float s1 = 0.f, s2 = 0.f;
+      float s1 = 0.f, m2 = 0.f;
+      for (int i = 0; i < p.stats_parts_in; ++i) s1 += __ldg(p.stats_in + mrow * p.stats_parts_in + i).x;
+      mean = s1 * p.ln_inv_c;
       for (int i = 0; i < p.stats_parts_in; ++i) {
         const float2 q = __ldg(p.stats_in + mrow * p.stats_parts_in + i);
-        s1 += q.x;
-        s2 += q.y;
+        const float dm = q.x * part_inv_n - mean;
+        m2 += q.y + part_n * dm * dm;
       }
-      mean = s1 * p.ln_inv_c;
-      rstd = rsqrtf(fmaxf(s2 * p.ln_inv_c - mean * mean, 0.f) + p.ln_eps);
+      rstd = rsqrtf(m2 * p.ln_inv_c + p.ln_eps);
     };
     if (ln_in && plain && pt0 < num_ptiles) {
       const long long m0 = static_cast<long long>(2 * w_mp + static_cast<int>(rank)) * BM + r;
@@ -356,7 +359,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       } else if (ln_in && valid) {
         stats_of(m, ln_mean, ln_rstd);
       }
-      float st_sum = 0.f, st_sq = 0.f;
+      // Row statistics for the fused LayerNorm of the consumer, SHIFTED by the first value of the slice: sums of (x - K) and
+      // (x - K)^2 do not cancel when the row mean is large against its spread (real checkpoints; E[x^2] - mean^2 would).
+      float st_sum = 0.f, st_sq = 0.f, st_K = 0.f;
+      bool st_have = false;
+      int st_n = 0;
       const T* resid_row = has_resid ? reinterpret_cast<const T*>(p.resid) + res_row * p.ld_resid : nullptr;
 
       // one 16-column chunk: LN-fold / bias / activation / layer-scale / residual / store
@@ -468,11 +475,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (int j = 0; j < 8; ++j) o.v[j] = Cvt<T>::pack(v[2 * j], v[2 * j + 1]);
             stg256(op, o);
             if (do_stats) {                           // statistics of the ROUNDED values the consumer will read
+              st_n += 16;
 #pragma unroll
               for (int j = 0; j < 8; ++j) {
                 const float2 f = Cvt<T>::unpack(o.v[j]);
-                st_sum += f.x + f.y;
-                st_sq = fmaf(f.x, f.x, fmaf(f.y, f.y, st_sq));
+                if (!st_have) {
+                  st_K = f.x;
+                  st_have = true;
+                }
+                const float d0 = f.x - st_K, d1 = f.y - st_K;
+                st_sum += d0 + d1;
+                st_sq = fmaf(d0, d0, fmaf(d1, d1, st_sq));
               }
             }
           } else {
@@ -482,8 +495,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 op[j] = h;
                 if (do_stats) {
                   const float f = Cvt<T>::to_f(h);
-                  st_sum += f;
-                  st_sq = fmaf(f, f, st_sq);
+                  if (!st_have) {
+                    st_K = f;
+                    st_have = true;
+                  }
+                  const float d0 = f - st_K;
+                  ++st_n;
+                  st_sum += d0;
+                  st_sq = fmaf(d0, d0, st_sq);
                 }
               }
           }
@@ -539,23 +558,32 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           rv_cur = rv_nxt;
         }
       }
-      if (do_stats && valid)
-        p.stats_out[static_cast<long long>(m) * p.stats_parts_out + (alt ? tc.n_tile * 2 + chalf : tc.n_tile * 4 + chalf * 2 + grp)] = make_float2(st_sum, st_sq);
+      if (do_stats && valid) {
+        // partial = (sum of the slice, sum of squared deviations from the slice's own mean); every slice has the same width
+        // (gemm_build checks N % BN == 0 for producers), which is all the consumer needs to combine them (Chan et al.)
+        const float nn = static_cast<float>(st_n > 0 ? st_n : 1);
+        const float part_sum = fmaf(nn, st_K, st_sum), part_m2 = fmaxf(st_sq - st_sum * st_sum / nn, 0.f);
+        p.stats_out[static_cast<long long>(m) * p.stats_parts_out + (alt ? tc.n_tile * 2 + chalf : tc.n_tile * 4 + chalf * 2 + grp)] = make_float2(part_sum, part_m2);
+      }
       if (nx_row >= 0) {                              // statistics of the next tile's row: the requests above have landed by now
-        float s1 = 0.f, s2 = 0.f;
+        float s1 = 0.f, m2 = 0.f;
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          if (i < p.stats_parts_in) s1 += nq[i].x;
+        for (int i = 4; i < p.stats_parts_in; ++i) s1 += __ldg(p.stats_in + nx_row * p.stats_parts_in + i).x;
+        nx_mean = s1 * p.ln_inv_c;
 #pragma unroll
         for (int i = 0; i < 4; ++i)
           if (i < p.stats_parts_in) {
-            s1 += nq[i].x;
-            s2 += nq[i].y;
+            const float dm = nq[i].x * part_inv_n - nx_mean;
+            m2 += nq[i].y + part_n * dm * dm;
           }
         for (int i = 4; i < p.stats_parts_in; ++i) {
           const float2 q = __ldg(p.stats_in + nx_row * p.stats_parts_in + i);
-          s1 += q.x;
-          s2 += q.y;
+          const float dm = q.x * part_inv_n - nx_mean;
+          m2 += q.y + part_n * dm * dm;
         }
-        nx_mean = s1 * p.ln_inv_c;
-        nx_rstd = rsqrtf(fmaxf(s2 * p.ln_inv_c - nx_mean * nx_mean, 0.f) + p.ln_eps);
+        nx_rstd = rsqrtf(m2 * p.ln_inv_c + p.ln_eps);
       }
     }
   }
@@ -619,7 +647,7 @@ int gemm_build(const GemmDesc& d, GemmOp* op, std::string* err) {
   a.stats_out = d.stats_out; a.stats_in = d.stats_in; a.stats_parts_in = d.stats_parts_in; a.colsum = d.colsum;
   a.ln_inv_c = d.ln_C > 0 ? 1.f / d.ln_C : 0.f; a.ln_eps = d.ln_eps;
   if ((d.stats_out || d.stats_in) && (d.a_mode != AMODE_PLAIN || d.remap_rows || d.shuffle_cout || d.out_fp32)) { *err = "gemm: LN fusion needs a plain 16-bit GEMM"; return -1; }
-  if (d.stats_in && (!d.colsum || d.stats_parts_in <= 0 || d.ln_C <= 0)) { *err = "gemm: LN consumer needs colsum / parts / C"; return -1; }
+  if (d.stats_in && (!d.colsum || d.stats_parts_in <= 0 || d.ln_C <= 0 || d.ln_C % d.stats_parts_in != 0)) { *err = "gemm: LN consumer needs colsum / parts / C (C a multiple of the partial count)"; return -1; }
   op->dtype = d.dtype;
   if ((d.remap_rows || d.shuffle_cout) && (d.IH <= 0 || d.IW <= 0 || d.M % (d.IH * d.IW) != 0)) {
     *err = "gemm: row remap needs IH/IW with M a multiple of IH*IW"; return -1;
@@ -677,6 +705,7 @@ int gemm_build(const GemmDesc& d, GemmOp* op, std::string* err) {
   }
 
   const int bn = pick_bn(d.N, m_tiles);
+  if (d.stats_out && d.N % bn != 0) { *err = "gemm: a LayerNorm-statistics producer needs N to be a multiple of its n-tile (equal-width partials)"; return -1; }
   op->bn = bn;
   a.n_tiles = (d.N + bn - 1) / bn;
   {
