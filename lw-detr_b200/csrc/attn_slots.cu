@@ -1,30 +1,33 @@
 // tcgen05 / TMA attention for head dims 16 and 32 - the ViT window attention (vit.py:130-137 with B' = 16B, N = 100) and
-// the ViT global attention at head dim 16 (tiny / small; vit.py:201-204).  At these head dims the kernel is bound by the
-// exponentials, not by the tensor core (16 MUFU.EX2 per clock and SM against <= 0.5 k clocks of MMA per 128x128 score
-// tile), so the design is organised around the softmax threads:
+// the ViT global attention (vit.py:201-204) of LW-DETR-tiny / small / medium / large.  At these head dims the kernel is
+// bound by the exponentials, not by the tensor core (16 MUFU.EX2 per clock and SM against <= 0.5 k clocks of MMA per
+// 128x128 score tile), so the design is organised around the softmax threads (profiles/r02_attn_history.md):
 //
-//   * FOUR independent "slots" per CTA (one CTA per SM).  A slot owns one 128-row query tile, its own 128 TMEM columns
-//     (S 64 fp32 | P 32 packed 16-bit | O dh fp32) and its own barrier set; keys are consumed in chunks of 64.
-//   * warps 0-3  : one DRIVER warp per slot (one elected lane): TMA loads of Q and of the K/V chunks straight out of the
-//                  packed [rows, 3C] qkv matrix, and all tcgen05.mma of the slot (S = Q K^T, O += P V with P read from TMEM).
-//   * warps 4-19 : 16 SOFTMAX warps, four per slot, ONE THREAD PER QUERY ROW (tcgen05.ld 32x32b hands thread t row t):
-//                  the row maximum, the lazy rescale decision (FlashAttention-4: the reference maximum only moves when
-//                  exceeded by 2^8) and the row sum need no cross-thread exchange at all.  Every scheduler hosts one
-//                  softmax warp of each slot, i.e. four independent instruction streams.
-//   * exp2: packed fp32x2 FMAs (fma.rn.f32x2) fold scale and max-subtraction; 3 of every 8 pairs take a degree-3
-//     polynomial on the FMA pipe instead of the MUFU (Cody-Waite split by the 1.5*2^23 magic add, exponent patched in with
-//     an integer add; max relative error 7.5e-5, an order of magnitude below the 16-bit rounding of P).  Measured on the
-//     B200 (tools/ubench/softmax_rate.cu, profiles/r02a_ubench_softmax.txt): 0.0486 clk/score/SM against the 0.0625
-//     MUFU floor; more than 3/8 makes the issue slots the bottleneck again.
+//   * FOUR independent "slots" per CTA (one CTA per SM, 20 warps).  A slot owns one 128-row query tile, its own 128 TMEM
+//     columns (S 64 fp32 | P 32 packed 16-bit | O dh fp32 | row sums 16) and its own barrier set; keys come in chunks of 64.
+//   * warps 0-15 : SOFTMAX warps, four per slot (slot = warp / 4, TMEM lane quarter = warp % 4), ONE THREAD PER QUERY ROW
+//                  (tcgen05.ld 32x32b hands thread t row t): the row maximum, the lazy rescale decision (FlashAttention-4:
+//                  the reference maximum only moves when exceeded by 2^8) and P need no cross-thread exchange at all.
+//                  Every scheduler hosts one softmax warp of each slot, i.e. four independent instruction streams.
+//   * warps 16-19: one DRIVER thread per slot: its tcgen05.mma (S = Q K^T, O += P V with P read from TMEM), its TMA loads
+//                  straight out of the packed [rows, 3C] qkv matrix (Q double-buffered one item ahead, K/V ring probed
+//                  without blocking) and the commits.  This lone thread is the slot's critical path (one dependent
+//                  instruction per 10-20 clocks): everything it does per chunk is incremental.
+//   * row sums out of the P V product (head dim 16): the B operand is [V | 1] with N = 32, the block of ones reached through
+//     the descriptor's leading byte offset (FUSED).
+//   * exp2: packed fp32x2 FMAs (fma.rn.f32x2) fold scale and max-subtraction.  A degree-3 polynomial exp2 on the FMA pipe
+//     (Cody-Waite split by the 1.5*2^23 magic add, max relative error 7.5e-5) can take PMASK/8 of the pairs; measured in
+//     the kernel it does not pay (the softmax threads are issue-bound before the two pipes overlap), so the default is 0.
 //   * setmaxnreg moves registers from the driver warps (96 -> 64) to the softmax warps (96 -> 104), which hold a 64-score row
 //     chunk.  The pool is per CTA: what the 16 softmax warps take (16*32*8) must not exceed what the 4 driver warps release.
 //
-// Two work decompositions share the code (template SHARED):
-//   SHARED = true  (sequences longer than one tile, e.g. 1600 tokens): the four slots of a CTA take up to four consecutive
-//                  query tiles of ONE (sequence, head) and walk the keys in lock step over ONE K/V ring filled by slot
-//                  0's driver - K/V are fetched once per CTA, not once per tile.
-//   SHARED = false (sequences of <= 128 tokens, e.g. the 100-token windows): every slot walks its own (sequence, head)
-//                  items with its own small K/V ring; the tail chunk only exponentiates the valid keys (104 instead of 128).
+// Work decompositions (templates SHARED / LONG):
+//   independent slots (default): every slot walks its own (sequence, head, query tile) items with its own K/V ring;
+//   SHARED = lock step: the four slots of a CTA take consecutive query tiles of ONE (sequence, head) over ONE K/V ring
+//            (fills round-robin over the four drivers);
+//   LONG   = sequences of more than one tile (1600 tokens): warps whose rows lie beyond the sequence only keep the barrier
+//            protocol going; one-tile sequences (the 100-token windows) instead defer an item's epilogue into the next
+//            item's first chunk, and their tail chunk only exponentiates the valid keys (104 instead of 128).
 // CTAs are persistent and walk their items with a fixed stride.
 #include "attn.h"
 #include "launch.h"
