@@ -387,7 +387,7 @@ __global__ void __launch_bounds__(THREADS, 1) attn_slots_kernel(const __grid_con
       // ---------------------------------------------------------------- driver of one slot: its tcgen05.mma, its TMA loads.
       // The slot's work is a flat stream of (item, chunk) steps; S is issued one chunk ahead of the softmax warps, P V follows
       // them, loads run ahead as far as the ring allows (non-blocking probe).  This thread's own instruction stream is the
-      // critical path of the slot - ncu of the first version (profiles/r02h_ncu_glb_small.txt) showed the softmax warps
+      // critical path of the slot - ncu of the first version (profiles/r02_attn_history.md) showed the softmax warps
       // waiting for S a quarter of their time while the lone driver thread worked through ~250 instructions per chunk at
       // one dependent instruction per 10-20 clocks - so everything per chunk is incremental: no divisions, no descriptor
       // rebuilds, stage / phase counters that wrap by comparison.  With the shared ring the four drivers take turns at the
@@ -834,7 +834,7 @@ static int slots_poly() {
 }
 
 // LWDETR_B200_SLOTS_MODE (A/B measurements): bit 0 = independent slots (own K/V ring each) for long sequences too,
-// bit 1 = fused row sums (head dim 16).  Default 3, measured on small / B = 32 global attention (profiles/r02j): lock-step +
+// bit 1 = fused row sums (head dim 16).  Default 3, measured on small / B = 32 global attention (profiles/r02_attn_history.md): lock-step +
 // separate sums 391 us, independent 360, lock-step + fused 358, independent + fused 336 (all with 3/8 polynomial exps).
 static int slots_mode() {
   static int v = [] {

@@ -9,7 +9,7 @@
 //    ([image][head][token][16], gemm_tc "head-major" epilogue), so everything one (image, head) can ever sample is
 //    ONE contiguous slab (51 KB at 40x40).  Persistent CTAs (one per SM, 20 warps) walk the (image, head) items: the
 //    slab is streamed - in bands of <= 1680 tokens - into a four-stage shared-memory ring with 1-D bulk copies
-//    (cp.async.bulk + mbarrier complete_tx; measured 7.0 TB/s at this chunk size, profiles/r02c_ubench_stream.txt),
+//    (cp.async.bulk + mbarrier complete_tx; measured 7.0 TB/s at this chunk size with tools/ubench/stream_rate.cu),
 //    the threads (two per (query, head): half of the samples each, all 16 channels) take the bilinear corners out of
 //    shared memory.  DRAM sees the value tensor exactly once, as a linear stream; the softmax over
 //    the L*P logits, the sampling-location arithmetic (incl. valid ratios of padded batches) and the weighted sum
@@ -62,7 +62,7 @@ __device__ __forceinline__ uint64_t shfl_xor1_b64(uint64_t v) {
   return (static_cast<uint64_t>(hi) << 32) | lo;
 }
 
-// ncu of the earlier versions of this kernel (profiles/r02d_ncu_msda_small.txt, r02g_ncu_msda_medium.txt) showed it bound by
+// ncu of the earlier versions of this kernel (history in DESIGN.md 3.2; current capture: profiles/r02_ncu_msda_medium.txt) showed it bound by
 // its own instruction stream and by a tail, not by memory: 735 instructions per (query, head) - a fifth of them integer
 // divisions of the item / pass bookkeeping, another third register shuffling around the 16-bit -> fp32 unpack - at 36 % issue
 // utilisation, with half-CTAs that each walked whole (image, head) items (3.46 items per half at medium / B = 64: 14 % tail).

@@ -14,8 +14,8 @@ sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(
 #   AC3     - 3x the deviation of a torch.autocast run of the same forward on the same synthetic weights (the
 #             reference's own low-precision mode; calibrated on tiny/small B=2 in the build container)
 # The test asserts the TIGHTER of the two wherever the CUDA path meets it on every config and batch size measured on the
-# B200 (profiles/r02_parity_baseline.json); the two exceptions are stated with their reason.
-#                      SURVEY    AC3       asserted (B<=2)  asserted (BASELINE batch)   measured max (profiles/r02_parity.json)
+# B200 (profiles/r02_parity_baseline_*.json); the two exceptions are stated with their reason.
+#                      SURVEY    AC3       asserted (B<=2)  asserted (BASELINE batch)   measured max (profiles/r02_parity_baseline_*.json)
 #   fp16 logits rel-L2 1.5e-3    1.8e-3    1.5e-3           1.5e-3                      6.8e-4  (B = 16..32, worst image)
 #   fp16 logits max    1.5e-2    2.1e-2    2.1e-2           2.1e-2                      1.2e-2 at B<=2, 1.42e-2 at B = 16..32
 #   fp16 boxes  max    2.0e-4    8.5e-4    8.5e-4           1.5e-3                      6.6e-4 at B<=2 (large), 1.05e-3 at B = 32 (large, aux)
