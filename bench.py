@@ -389,7 +389,7 @@ def measure_config(cfg_name, batch, dtype_name, steps, warmup, dev, rank, world,
                     out["pred_boxes"].record_stream(d2h_stream)
             if d2h_stream is not None:
                 main_stream.wait_stream(d2h_stream)                # the timed region ends when the last read-back has landed
-        run(3)
+        run(6)                                             # warm-up: also lets the caching allocator reach its steady state (outputs are freed a stream event later)
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
