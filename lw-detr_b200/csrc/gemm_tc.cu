@@ -48,7 +48,7 @@ __device__ __forceinline__ float gelu_erf(float x) {
 
 // The same exact-erf GELU for a PAIR on the packed fp32x2 pipe, without the MUFU: gelu(x) = x * (0.5 + xc * q(xc^2)), xc = x
 // clamped to [-4.5, 4.5], q a degree-9 polynomial fitted to erf(x/sqrt2) / (2x) (weighted least squares at Chebyshev nodes;
-// fp32 Horner: max |error| 7.4e-5 at |x| ~ 4.46 where gelu ~ 4.46, < 1e-6 for |x| < 3; beyond the clamp Phi(-4.5) = 3.4e-6
+// fp32 Horner: max |error| 7.4e-5 at |x| ~ 4.46 where gelu ~ 4.46, < 1e-5 for |x| < 3 (tests/test_numerics_cpu.py); beyond the clamp Phi(-4.5) = 3.4e-6
 // multiplies x).  16 instructions per pair (8 per element) against 14 per element for gelu_erf - the fc1 epilogue is bound by
 // its instruction count, not by the tensor core.
 __device__ __forceinline__ uint64_t gelu_erf2(uint64_t x2) {
